@@ -1,0 +1,616 @@
+"""Benchmark / parity workloads, written as *user scripts* against the public API.
+
+Every builder takes an ``api`` namespace that provides ``Problem, Guess,
+Condition, Dynamics`` -- the drop-in facade (``OpenGoddard.optimize``), the
+numpy oracle (``oracle.og_numpy``) or, inside the build container, the real
+reference module -- and returns a fully set-up problem (guess written, callbacks
+assigned).  The same definition therefore drives the CUDA path, the oracle and
+the reference, which is what makes the parity tests meaningful.
+
+The optimal-control problems are the ones `BASELINE.json:configs` names; the
+physics follows the reference's shipped example scripts (cited per builder) with
+the same operation order, so constraint vectors agree with the examples to the
+last bit, but the node counts are parameters.
+
+Synthetic instance batches (`make_batch`) follow SURVEY.md section 8(d).
+"""
+from collections import namedtuple
+
+import numpy as np
+
+Workload = namedtuple("Workload", "name prob obj sanitize")
+
+SEED0 = 20261017
+
+
+# --------------------------------------------------------------------------
+# cfg1: Brachistochrone (reference: examples/01_Brachistochrone_Problem.py:9-91)
+# --------------------------------------------------------------------------
+class _Bead:
+    def __init__(self):
+        self.g = 1.0
+        self.l = 1.0
+
+
+def brachistochrone(api, nodes=(20,)):
+    bead = _Bead()
+    prob = api.Problem([0.0, 2.0], list(nodes), [3], [1], 30)
+
+    def dyn(prob, obj, section):
+        v = prob.states(2, section)
+        th = prob.controls(0, section)
+        d = api.Dynamics(prob, section)
+        d[0] = v * np.sin(th)
+        d[1] = v * np.cos(th)
+        d[2] = obj.g * np.cos(th)
+        return d()
+
+    def eq(prob, obj):
+        x = prob.states_all_section(0)
+        y = prob.states_all_section(1)
+        v = prob.states_all_section(2)
+        r = api.Condition()
+        r.equal(x[0], 0.0)
+        r.equal(y[0], 0.0)
+        r.equal(v[0], 0.0)
+        r.equal(x[-1], obj.l)
+        return r()
+
+    def ineq(prob, obj):
+        y = prob.states_all_section(1)
+        th = prob.controls_all_section(0)
+        tf = prob.time_final(-1)
+        r = api.Condition()
+        r.lower_bound(tf, 0.1)
+        r.lower_bound(y, 0)
+        r.lower_bound(th, 0)
+        return r()
+
+    def cost(prob, obj):
+        return prob.time_final(-1)
+
+    def cost_grad(prob, obj):
+        g = api.Condition(prob.number_of_variables)
+        g.change_value(prob.index_time_final(-1), 1)
+        return g()
+
+    t = prob.time_all_section
+    prob.set_states_all_section(0, api.Guess.linear(t, 0.0, bead.l))
+    prob.set_states_all_section(1, api.Guess.linear(t, 0.0, bead.l / np.sqrt(3)))
+    prob.set_controls_all_section(0, api.Guess.linear(t, np.deg2rad(30), np.deg2rad(30)))
+    prob.dynamics = [dyn]
+    prob.knot_states_smooth = []
+    prob.cost = cost
+    prob.cost_derivative = cost_grad
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("brachistochrone", prob, bead, None)
+
+
+# --------------------------------------------------------------------------
+# cfg2 / cfg3: Goddard rocket (reference: examples/04_Goddard_0knot.py:10-97,
+# examples/05_Goddard_1knot.py:10-175)
+# --------------------------------------------------------------------------
+class _GoddardRocket:
+    def __init__(self):
+        self.g0 = 1.0
+        self.H0, self.V0, self.M0 = 1.0, 0.0, 1.0
+        Tc, Vc, Mc = 3.5, 620, 0.6
+        self.Hc = 500
+        self.c = 0.5 * np.sqrt(self.g0 * self.H0)
+        self.Mf = Mc * self.M0
+        self.Dc = 0.5 * Vc * self.M0 / self.g0
+        self.T_max = Tc * self.g0 * self.M0
+
+
+def _goddard_callbacks(api, two_phase):
+    def dyn(prob, obj, section):
+        h = prob.states(0, section)
+        v = prob.states(1, section)
+        m = prob.states(2, section)
+        T = prob.controls(0, section)
+        drag = 1 * obj.Dc * v ** 2 * np.exp(-obj.Hc * (h - obj.H0) / obj.H0)
+        grav = obj.g0 * (obj.H0 / h) ** 2
+        d = api.Dynamics(prob, section)
+        d[0] = v
+        d[1] = (T - drag) / m - grav
+        d[2] = - T / obj.c
+        return d()
+
+    def eq(prob, obj):
+        h = prob.states_all_section(0)
+        v = prob.states_all_section(1)
+        m = prob.states_all_section(2)
+        r = api.Condition()
+        r.equal(h[0], obj.H0)
+        r.equal(v[0], obj.V0)
+        r.equal(m[0], obj.M0)
+        r.equal(v[-1], 0.0)
+        r.equal(m[-1], obj.Mf)
+        if two_phase:
+            r.equal(prob.time_final(0), 0.075)
+        return r()
+
+    def ineq(prob, obj):
+        h = prob.states_all_section(0)
+        v = prob.states_all_section(1)
+        m = prob.states_all_section(2)
+        T = prob.controls_all_section(0)
+        tf = prob.time_final(-1)
+        r = api.Condition()
+        r.lower_bound(h, obj.H0)
+        r.lower_bound(v, 0.0)
+        r.lower_bound(m, obj.Mf)
+        r.lower_bound(T, 0.0)
+        r.lower_bound(tf, 0.1)
+        if two_phase:
+            r.lower_bound(prob.time_final(0), 0.05)
+        r.upper_bound(m, obj.M0)
+        r.upper_bound(T, obj.T_max)
+        return r()
+
+    return dyn, eq, ineq
+
+
+def goddard(api, nodes=(50,)):
+    """Goddard 0-knot: 1 phase, 3 states (h, v, m), 1 control (thrust)."""
+    ro = _GoddardRocket()
+    prob = api.Problem([0.0, 0.3], list(nodes), [3], [1], 30)
+    dyn, eq, ineq = _goddard_callbacks(api, two_phase=False)
+
+    def cost(prob, obj):
+        return -prob.states_all_section(0)[-1]
+
+    t = prob.time_all_section
+    prob.set_states_all_section(0, api.Guess.cubic(t, 1.0, 0.0, 1.010, 0.0))
+    prob.set_states_all_section(1, api.Guess.linear(t, 0.0, 0.0))
+    prob.set_states_all_section(2, api.Guess.cubic(t, 1.0, -0.6, 0.6, 0.0))
+    prob.set_controls_all_section(0, api.Guess.cubic(t, 3.5, 0.0, 0.0, 0.0))
+    prob.dynamics = [dyn]
+    prob.knot_states_smooth = []
+    prob.cost = cost
+    prob.cost_derivative = None
+    prob.equality = eq
+    prob.inequality = ineq
+
+    def sanitize(prob, P):
+        n0 = prob.nodes[0]
+        P[:, 0:n0] = np.maximum(P[:, 0:n0], 0.99)          # h >= 0.99
+        P[:, 2 * n0:3 * n0] = np.maximum(P[:, 2 * n0:3 * n0], 0.1)  # m >= 0.1
+        return P
+
+    return Workload("goddard", prob, ro, sanitize)
+
+
+def goddard_knot(api, nodes=(25, 25)):
+    """Goddard 1-knot: 2 phases joined by smooth-state knot rows; state 0 carries a
+    canonical unit of 0.1 and the cost reads ``states_all_section(-1)`` exactly as
+    the shipped script does."""
+    ro = _GoddardRocket()
+    prob = api.Problem([0.0, 0.1, 0.3], list(nodes), [3, 3], [1, 1], 50)
+    prob.set_unit_states_all_section(0, 0.1)
+    dyn, eq, ineq = _goddard_callbacks(api, two_phase=True)
+
+    def cost(prob, obj):
+        return -prob.states_all_section(-1)[-1]
+
+    def cost_grad(prob, obj):
+        g = api.Condition(prob.number_of_variables)
+        g.change_value(prob.index_states(0, -1, -1), -1)
+        return g()
+
+    t = prob.time_all_section
+    prob.set_states_all_section(0, api.Guess.cubic(t, 1.0, 0.0, 1.010, 0.0))
+    prob.set_states_all_section(1, api.Guess.linear(t, 0.0, 0.0))
+    prob.set_states_all_section(2, np.hstack((api.Guess.linear(prob.time[0], 1.0, 0.6),
+                                              api.Guess.linear(prob.time[1], 0.6, 0.6))))
+    prob.set_controls_all_section(0, np.hstack((api.Guess.linear(prob.time[0], 3.5, 3.5),
+                                                api.Guess.linear(prob.time[1], 0.0, 0.0))))
+    prob.dynamics = [dyn, dyn]
+    prob.knot_states_smooth = [True]
+    prob.cost = cost
+    prob.cost_derivative = cost_grad
+    prob.equality = eq
+    prob.inequality = ineq
+
+    def sanitize(prob, P):
+        u0 = prob.unit_states[0][0]
+        for s in range(prob.number_of_section):
+            a = prob.index_states(0, s)
+            P[:, a:a + prob.nodes[s]] = np.maximum(P[:, a:a + prob.nodes[s]], 0.99 / u0)
+            a = prob.index_states(2, s)
+            P[:, a:a + prob.nodes[s]] = np.maximum(P[:, a:a + prob.nodes[s]], 0.1)
+        return P
+
+    return Workload("goddard_knot", prob, ro, sanitize)
+
+
+# --------------------------------------------------------------------------
+# cfg4: polar-coordinate multi-stage ascent
+# (reference: examples/09_Rocket_Ascent_Polar_TSTO.py:10-293)
+# --------------------------------------------------------------------------
+class _StagedLauncher:
+    GMe = 3.986004418 * 10 ** 14
+    Re = 6371.0 * 1000
+    g0 = 9.80665
+
+    def __init__(self, nstage_sections):
+        self.M0 = [20000.0, 1000.0]
+        self.Mdry = [2000, 200]
+        self.Cd = [0.2, 0.2]
+        self.A = [3.14, 3.14]
+        self.Isp = [300.0, 350.0]
+        self.Tmax = [self.M0[0] * self.g0 * 1.5, self.M0[1] * self.g0 * 1.5]
+        self.MaxG = 8.0
+        self.Rtarget = self.Re + 500.0 * 1000
+        self.Vtarget = np.sqrt(self.GMe / self.Rtarget)
+        # section -> stage map (2-phase: [0, 1]; 3-phase extension: [0, 1, 1])
+        self.stage = nstage_sections
+
+    def air_density(self, h):
+        beta = 1 / 8500.0
+        rho0 = 1.225
+        h[h < -100.0] = -100.0
+        return rho0 * np.exp(-beta * h)
+
+
+def _polar_dynamics(api):
+    def dyn(prob, obj, section):
+        R = prob.states(0, section)
+        Vr = prob.states(2, section)
+        Vt = prob.states(3, section)
+        m = prob.states(4, section)
+        Tr = prob.controls(0, section)
+        Tt = prob.controls(1, section)
+        st = obj.stage[section]
+        rho = obj.air_density(R - obj.Re)
+        Dr = 0.5 * rho * Vr * np.sqrt(Vr ** 2 + Vt ** 2) * obj.Cd[st] * obj.A[st]
+        Dt = 0.5 * rho * Vt * np.sqrt(Vr ** 2 + Vt ** 2) * obj.Cd[st] * obj.A[st]
+        grav = obj.g0 * (obj.Re / R) ** 2
+        d = api.Dynamics(prob, section)
+        d[0] = Vr
+        d[1] = Vt / R
+        d[2] = Tr / m - Dr / m - grav + Vt ** 2 / R
+        d[3] = Tt / m - Dt / m - (Vr * Vt) / R
+        d[4] = - np.sqrt(Tr ** 2 + Tt ** 2) / obj.g0 / obj.Isp[st]
+        return d()
+    return dyn
+
+
+def _polar_setup_units(prob, veh):
+    uR = veh.Re
+    uV = np.sqrt(veh.GMe / veh.Re)
+    um = veh.M0[0]
+    ut = uR / uV
+    uT = um * uR / ut ** 2
+    for k, u in enumerate((uR, 1, uV, uV, um)):
+        prob.set_unit_states_all_section(k, u)
+    prob.set_unit_controls_all_section(0, uT)
+    prob.set_unit_controls_all_section(1, uT)
+    prob.set_unit_time(ut)
+
+
+def polar_tsto(api, nodes=(20, 20)):
+    """Two-stage polar ascent, 2 phases; knot linkage lives in the user equality
+    (``knot_states_smooth=[False]``)."""
+    veh = _StagedLauncher([0, 1])
+    prob = api.Problem([0.0, 100, 200], list(nodes), [5, 5], [2, 2], 40)
+    _polar_setup_units(prob, veh)
+    dyn = _polar_dynamics(api)
+
+    def eq(prob, obj):
+        Vr = prob.states_all_section(2)
+        Vt = prob.states_all_section(3)
+        R0, R1 = prob.states(0, 0), prob.states(0, 1)
+        th0, th1 = prob.states(1, 0), prob.states(1, 1)
+        Vr0, Vr1 = prob.states(2, 0), prob.states(2, 1)
+        Vt0, Vt1 = prob.states(3, 0), prob.states(3, 1)
+        m0, m1 = prob.states(4, 0), prob.states(4, 1)
+        uR, uV, um = prob.unit_states[0][0], prob.unit_states[0][2], prob.unit_states[0][4]
+        r = api.Condition()
+        r.equal(R0[0], obj.Re, unit=uR)
+        r.equal(th0[0], 0.0)
+        r.equal(Vr0[0], 0.0, unit=uV)
+        r.equal(Vt0[0], 0.0, unit=uV)
+        r.equal(m0[0], obj.M0[0], unit=um)
+        r.equal(m1[0], obj.M0[1], unit=um)
+        r.equal(R1[-1], obj.Rtarget, unit=uR)
+        r.equal(Vr[-1], 0.0, unit=uV)
+        r.equal(Vt[-1], obj.Vtarget, unit=uV)
+        r.equal(R1[0], R0[-1], unit=uR)
+        r.equal(th1[0], th0[-1])
+        r.equal(Vr1[0], Vr0[-1], unit=uV)
+        r.equal(Vt1[0], Vt0[-1], unit=uV)
+        return r()
+
+    def ineq(prob, obj):
+        R = prob.states_all_section(0)
+        Vr = prob.states_all_section(2)
+        Vt = prob.states_all_section(3)
+        m = prob.states_all_section(4)
+        Tr = prob.controls_all_section(0)
+        Tt = prob.controls_all_section(1)
+        Tr0, Tr1 = prob.controls(0, 0), prob.controls(0, 1)
+        Tt0, Tt1 = prob.controls(1, 0), prob.controls(1, 1)
+        rho = obj.air_density(R - obj.Re)
+        Dr0 = 0.5 * rho * Vr * np.sqrt(Vr ** 2 + Vt ** 2) * obj.Cd[0] * obj.A[0]
+        Dt0 = 0.5 * rho * Vt * np.sqrt(Vr ** 2 + Vt ** 2) * obj.Cd[0] * obj.A[0]
+        Dr1 = 0.5 * rho * Vr * np.sqrt(Vr ** 2 + Vt ** 2) * obj.Cd[1] * obj.A[1]
+        Dt1 = 0.5 * rho * Vt * np.sqrt(Vr ** 2 + Vt ** 2) * obj.Cd[1] * obj.A[1]
+        a_r0 = (Tr - Dr0) / m
+        a_t0 = (Tt - Dt0) / m
+        a_mag0 = np.sqrt(a_r0 ** 2 + a_t0 ** 2)
+        a_r1 = (Tr - Dr1) / m
+        a_t1 = (Tt - Dt1) / m
+        a_mag1 = np.sqrt(a_r1 ** 2 + a_t1 ** 2)
+        T0 = np.sqrt(Tr0 ** 2 + Tt0 ** 2)
+        T1 = np.sqrt(Tr1 ** 2 + Tt1 ** 2)
+        r = api.Condition()
+        r.lower_bound(R, obj.Re, unit=prob.unit_states[0][0])
+        r.upper_bound(T0, obj.Tmax[0], unit=prob.unit_controls[0][0])
+        r.upper_bound(T1, obj.Tmax[1], unit=prob.unit_controls[0][0])
+        r.upper_bound(a_mag0, obj.MaxG * obj.g0)
+        r.upper_bound(a_mag1, obj.MaxG * obj.g0)
+        return r()
+
+    def cost(prob, obj):
+        return -prob.states(4, 1)[-1] / prob.unit_states[1][4]
+
+    t = prob.time_all_section
+    G = api.Guess
+    prob.set_states_all_section(0, G.cubic(t, veh.Re, 0.0, veh.Rtarget, 0.0))
+    prob.set_states_all_section(1, G.cubic(t, 0.0, 0.0, np.deg2rad(25.0), 0.0))
+    prob.set_states_all_section(2, G.linear(t, 0.0, 0.0))
+    prob.set_states_all_section(3, G.linear(t, 0.0, veh.Vtarget))
+    # the shipped script hands a 2x-long mass guess; only the first sum(nodes) are used
+    prob.set_states_all_section(4, np.hstack((G.cubic(t, veh.M0[0], -0.6, veh.Mdry[0], 0.0),
+                                              G.cubic(t, veh.M0[1], -0.6, veh.Mdry[1], 0.0))))
+    Tr_guess = np.hstack((G.cubic(prob.time[0], veh.Tmax[0] * 9 / 10, 0.0, 0.0, 0.0),
+                          G.cubic(prob.time[1], veh.Tmax[1] * 9 / 10, 0.0, 0.0, 0.0)))
+    prob.set_controls_all_section(0, Tr_guess)
+    prob.set_controls_all_section(1, Tr_guess)   # (sic) the shipped script reuses Tr here
+    prob.set_states_bounds_all_section(0, veh.Re, None)
+    prob.set_states_bounds(4, 0, veh.Mdry[0], veh.M0[0])
+    prob.set_states_bounds(4, 1, 1.0, veh.M0[1])
+    prob.set_controls_bounds(0, 0, -veh.Tmax[1], veh.Tmax[0])
+    prob.set_controls_bounds(1, 0, -veh.Tmax[1], veh.Tmax[0])
+    prob.set_controls_bounds(0, 1, -veh.Tmax[1], veh.Tmax[1])
+    prob.set_controls_bounds(1, 1, -veh.Tmax[1], veh.Tmax[1])
+    prob.dynamics = [dyn, dyn]
+    prob.knot_states_smooth = [False]
+    prob.cost = cost
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("polar_tsto", prob, veh, None)
+
+
+def polar_3phase(api, nodes=(40, 40, 40)):
+    """cfg4: a *synthetic* 3-phase extension of the two-stage polar ascent (the
+    shipped example has 2 phases; SURVEY.md section 2.3 note ii): stage 1 burn,
+    stage 2 first burn, stage 2 second burn.  Knot 0 (staging, mass reset) is
+    linked in the user equality; knot 1 uses the built-in smooth-state knot rows
+    (``knot_states_smooth=[False, True]``)."""
+    veh = _StagedLauncher([0, 1, 1])
+    prob = api.Problem([0.0, 100, 160, 220], list(nodes), [5, 5, 5], [2, 2, 2], 40)
+    _polar_setup_units(prob, veh)
+    dyn = _polar_dynamics(api)
+
+    def eq(prob, obj):
+        uR, uV, um = prob.unit_states[0][0], prob.unit_states[0][2], prob.unit_states[0][4]
+        first = [prob.states(k, 0) for k in range(5)]
+        second = [prob.states(k, 1) for k in range(5)]
+        last = [prob.states(k, 2) for k in range(5)]
+        r = api.Condition()
+        r.equal(first[0][0], obj.Re, unit=uR)
+        r.equal(first[1][0], 0.0)
+        r.equal(first[2][0], 0.0, unit=uV)
+        r.equal(first[3][0], 0.0, unit=uV)
+        r.equal(first[4][0], obj.M0[0], unit=um)
+        r.equal(second[4][0], obj.M0[1], unit=um)
+        r.equal(last[0][-1], obj.Rtarget, unit=uR)
+        r.equal(last[2][-1], 0.0, unit=uV)
+        r.equal(last[3][-1], obj.Vtarget, unit=uV)
+        r.equal(second[0][0], first[0][-1], unit=uR)
+        r.equal(second[1][0], first[1][-1])
+        r.equal(second[2][0], first[2][-1], unit=uV)
+        r.equal(second[3][0], first[3][-1], unit=uV)
+        return r()
+
+    def ineq(prob, obj):
+        R = prob.states_all_section(0)
+        Vr = prob.states_all_section(2)
+        Vt = prob.states_all_section(3)
+        m = prob.states_all_section(4)
+        Tr = prob.controls_all_section(0)
+        Tt = prob.controls_all_section(1)
+        rho = obj.air_density(R - obj.Re)
+        speed = np.sqrt(Vr ** 2 + Vt ** 2)
+        Dr = 0.5 * rho * Vr * speed * obj.Cd[0] * obj.A[0]
+        Dt = 0.5 * rho * Vt * speed * obj.Cd[0] * obj.A[0]
+        a_mag = np.sqrt(((Tr - Dr) / m) ** 2 + ((Tt - Dt) / m) ** 2)
+        r = api.Condition()
+        r.lower_bound(R, obj.Re, unit=prob.unit_states[0][0])
+        for s in range(3):
+            Ts = np.sqrt(prob.controls(0, s) ** 2 + prob.controls(1, s) ** 2)
+            r.upper_bound(Ts, obj.Tmax[obj.stage[s]], unit=prob.unit_controls[0][0])
+        r.upper_bound(a_mag, obj.MaxG * obj.g0)
+        r.lower_bound(prob.time_final(0), 30.0, unit=prob.unit_time)
+        return r()
+
+    def cost(prob, obj):
+        return -prob.states(4, 2)[-1] / prob.unit_states[2][4]
+
+    t = prob.time_all_section
+    G = api.Guess
+    n0, n1, n2 = nodes
+    prob.set_states_all_section(0, G.cubic(t, veh.Re, 0.0, veh.Rtarget, 0.0))
+    prob.set_states_all_section(1, G.cubic(t, 0.0, 0.0, np.deg2rad(25.0), 0.0))
+    prob.set_states_all_section(2, G.linear(t, 0.0, 0.0))
+    prob.set_states_all_section(3, G.linear(t, 0.0, veh.Vtarget))
+    t12 = np.concatenate((prob.time[1], prob.time[2]))
+    prob.set_states_all_section(4, np.hstack((G.linear(prob.time[0], veh.M0[0], veh.Mdry[0]),
+                                              G.linear(t12, veh.M0[1], veh.Mdry[1]))))
+    Tg = np.hstack((G.cubic(prob.time[0], veh.Tmax[0] * 9 / 10, 0.0, 0.0, 0.0),
+                    G.cubic(t12, veh.Tmax[1] * 9 / 10, 0.0, 0.0, 0.0)))
+    prob.set_controls_all_section(0, Tg)
+    prob.set_controls_all_section(1, Tg * 0.25)
+    prob.set_states_bounds_all_section(0, veh.Re, None)
+    prob.set_states_bounds(4, 0, veh.Mdry[0], veh.M0[0])
+    prob.set_states_bounds(4, 1, 1.0, veh.M0[1])
+    prob.set_states_bounds(4, 2, 1.0, veh.M0[1])
+    for s in range(3):
+        hi = veh.Tmax[veh.stage[s]]
+        prob.set_controls_bounds(0, s, -veh.Tmax[1], hi)
+        prob.set_controls_bounds(1, s, -veh.Tmax[1], hi)
+    prob.dynamics = [dyn, dyn, dyn]
+    prob.knot_states_smooth = [False, True]
+    prob.cost = cost
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("polar_3phase", prob, veh, None)
+
+
+# --------------------------------------------------------------------------
+# cfg5: low-thrust orbit transfer with a running (integrated) cost
+# (reference: examples/10_Low_Thrust_Orbit_Transfer.py:10-168)
+# --------------------------------------------------------------------------
+class _Spacecraft:
+    def __init__(self):
+        self.u_max = 0.01
+        self.r0, self.vr0, self.vt0 = 1.0, 0.0, 1.0
+        self.rf, self.vrf, self.vtf = 4.0, 0.0, 0.5
+        self.tf_max = 55
+
+
+def low_thrust(api, nodes=(100,)):
+    sc = _Spacecraft()
+    prob = api.Problem([0.0, 10.0], list(nodes), [3], [4], 10)
+
+    def dyn(prob, obj, section):
+        r = prob.states(0, section)
+        vr = prob.states(1, section)
+        vt = prob.states(2, section)
+        ur1 = prob.controls(0, section)
+        ur2 = prob.controls(1, section)
+        ut1 = prob.controls(2, section)
+        ut2 = prob.controls(3, section)
+        d = api.Dynamics(prob, section)
+        d[0] = vr
+        d[1] = vt ** 2 / r - 1 / r ** 2 + (ur1 - ur2)
+        d[2] = - vr * vt / r + (ut1 - ut2)
+        return d()
+
+    def eq(prob, obj):
+        r = prob.states_all_section(0)
+        vr = prob.states_all_section(1)
+        vt = prob.states_all_section(2)
+        c = api.Condition()
+        c.equal(r[0], obj.r0)
+        c.equal(vr[0], obj.vr0)
+        c.equal(vt[0], obj.vt0)
+        c.equal(r[-1], obj.rf)
+        c.equal(vr[-1], obj.vrf)
+        c.equal(vt[-1], obj.vtf)
+        return c()
+
+    def ineq(prob, obj):
+        r = prob.states_all_section(0)
+        ur1 = prob.controls_all_section(0)
+        ur2 = prob.controls_all_section(1)
+        ut1 = prob.controls_all_section(2)
+        ut2 = prob.controls_all_section(3)
+        tf = prob.time_final(-1)
+        c = api.Condition()
+        c.lower_bound(r, obj.r0)
+        c.lower_bound(ur1, 0.0)
+        c.lower_bound(ut1, 0.0)
+        c.lower_bound(ur2, 0.0)
+        c.lower_bound(ut2, 0.0)
+        c.lower_bound(tf, 0.0)
+        c.upper_bound(r, obj.rf)
+        c.upper_bound(ur1, obj.u_max)
+        c.upper_bound(ut1, obj.u_max)
+        c.upper_bound(ur2, obj.u_max)
+        c.upper_bound(ut2, obj.u_max)
+        c.upper_bound(tf, obj.tf_max)
+        return c()
+
+    def cost(prob, obj):
+        return 0.0
+
+    def running(prob, obj):
+        ur1 = prob.controls_all_section(0)
+        ur2 = prob.controls_all_section(1)
+        ut1 = prob.controls_all_section(2)
+        ut2 = prob.controls_all_section(3)
+        return (ur1 + ur2) + (ut1 + ut2)
+
+    t = prob.time_all_section
+    G = api.Guess
+    prob.set_states_all_section(0, G.linear(t, sc.r0, sc.rf))
+    prob.set_states_all_section(1, G.linear(t, sc.vr0, sc.vrf))
+    prob.set_states_all_section(2, G.linear(t, sc.vt0, sc.vtf))
+    prob.set_controls_all_section(0, G.linear(t, sc.u_max, sc.u_max))
+    prob.set_controls_all_section(2, G.linear(t, sc.u_max, sc.u_max))
+    prob.dynamics = [dyn]
+    prob.knot_states_smooth = []
+    prob.cost = cost
+    prob.running_cost = running
+    prob.equality = eq
+    prob.inequality = ineq
+
+    def sanitize(prob, P):
+        n0 = prob.nodes[0]
+        P[:, 0:n0] = np.maximum(P[:, 0:n0], 0.5)            # r >= 0.5
+        return P
+
+    return Workload("low_thrust", prob, sc, sanitize)
+
+
+# name -> (builder, default nodes) for the BASELINE.json configs
+CONFIGS = {
+    "cfg1_brachistochrone20": (brachistochrone, (20,)),
+    "cfg2_goddard50": (goddard, (50,)),
+    "cfg3_goddard_knot30x2": (goddard_knot, (30, 30)),
+    "cfg4_polar3x40": (polar_3phase, (40, 40, 40)),
+    "cfg5_lowthrust128": (low_thrust, (128,)),
+    # the shipped example sizes (used by the parity tests against the examples)
+    "ex05_goddard_knot25x2": (goddard_knot, (25, 25)),
+    "ex09_polar_tsto20x2": (polar_tsto, (20, 20)),
+    "ex10_lowthrust100": (low_thrust, (100,)),
+}
+
+
+def build(name, api):
+    fn, nodes = CONFIGS[name]
+    return fn(api, nodes)
+
+
+def bounds_arrays(prob):
+    """``prob.bounds`` (list of (lb|None, ub|None)) -> two float64 arrays with +-inf."""
+    lb = np.array([-np.inf if b[0] is None else float(b[0]) for b in prob.bounds])
+    ub = np.array([np.inf if b[1] is None else float(b[1]) for b in prob.bounds])
+    return lb, ub
+
+
+def make_batch(wl, B, first=0, seed0=SEED0):
+    """Seeded synthetic instance batch: instance ``b`` is the
+    shipped guess with 1 % multiplicative Gaussian jitter on every state/control
+    entry and +-5 % uniform jitter on the final times, clipped into the bounds.
+    One ``default_rng(seed0 + b)`` per instance so any sub-range is reproducible."""
+    prob = wl.prob
+    n = int(prob.number_of_variables)
+    nsec = int(prob.number_of_section)
+    p0 = np.asarray(prob.p, dtype=np.float64)
+    lb, ub = bounds_arrays(prob)
+    P = np.empty((B, n), dtype=np.float64)
+    for i in range(B):
+        rng = np.random.default_rng(seed0 + first + i)
+        z = rng.standard_normal(n - nsec)
+        u = rng.uniform(-1.0, 1.0, nsec)
+        P[i, :n - nsec] = p0[:n - nsec] * (1.0 + 0.01 * z)
+        P[i, n - nsec:] = p0[n - nsec:] * (1.0 + 0.05 * u)
+    if wl.sanitize is not None:
+        P = wl.sanitize(prob, P)
+    np.clip(P, lb, ub, out=P)
+    return P
