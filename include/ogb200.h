@@ -1,0 +1,156 @@
+/* ogb200.h -- C ABI of libogb200.so, the B200 (sm_100a) engine behind the
+ * `OpenGoddard.optimize` facade.
+ *
+ * The reference (istellartech/OpenGoddard) is pure Python and has no FFI; its
+ * boundary for the hot path is the set of Python closures `Problem.solve` hands to
+ * SciPy (reference OpenGoddard/optimize.py:670-749).  Each entry point below cites
+ * the reference code it replaces.  All `double*` arguments are CUDA DEVICE pointers
+ * (e.g. torch.Tensor.data_ptr()) unless the name ends in `_h`; the caller owns every
+ * buffer; every launch is enqueued on the given stream and does not synchronise.
+ * Return value: 0 = ok, negative = error (text via ogb_last_error()).
+ *
+ * One *eval* (the benchmark unit) = the stacked vector c = [c_eq ; c_ineq ; cost]
+ * at one decision vector p plus its dense forward-difference Jacobian with respect
+ * to all nvars variables -- what SLSQP asks for in mode -1
+ * (scipy/optimize/_slsqp_py.py:532-534).
+ */
+#ifndef OGB200_H
+#define OGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGB_VERSION 100
+
+/* ---- expression tapes -----------------------------------------------------
+ * User callbacks (dynamics / equality / inequality / cost / running_cost; reference
+ * optimize.py:674,685,703,706,727) are traced once on the host into straight-line
+ * register programs.  One instruction = one 64-bit word:
+ *     op[63:56]  dst[55:42]  a[41:28]  b[27:14]  c[13:0]
+ * A *node program* runs once per LGL node: OGB_LDP reads block `a` (state or control
+ * number within the phase) of the decision vector at that node.  The *scalar
+ * program* runs once per decision vector: OGB_LDP reads variable `a` of p.          */
+enum ogb_opcode {
+    OGB_NOP = 0,
+    OGB_LDP = 1,   /* r[dst] = input(a)                                   */
+    OGB_LDC = 2,   /* r[dst] = consts[a]                                  */
+    OGB_OUT = 3,   /* output slot `dst` = r[a]                            */
+    OGB_ADD = 4, OGB_SUB = 5, OGB_MUL = 6, OGB_DIV = 7,
+    OGB_POW = 8, OGB_MIN = 9, OGB_MAX = 10, OGB_ATAN2 = 11,
+    OGB_LT = 12, OGB_LE = 13, OGB_GT = 14, OGB_GE = 15, OGB_EQ = 16, OGB_NE = 17,
+    OGB_SEL = 18,  /* r[dst] = r[a] != 0 ? r[b] : r[c]                    */
+    OGB_NEG = 19, OGB_SQRT = 20, OGB_EXP = 21, OGB_LOG = 22, OGB_SIN = 23,
+    OGB_COS = 24, OGB_TAN = 25, OGB_ABS = 26, OGB_SQUARE = 27, OGB_RECIP = 28,
+    OGB_ASIN = 29, OGB_ACOS = 30, OGB_ATAN = 31, OGB_SINH = 32, OGB_COSH = 33,
+    OGB_TANH = 34, OGB_LOG10 = 35, OGB_SIGN = 36, OGB_FLOOR = 37, OGB_CEIL = 38,
+    OGB_AND = 39, OGB_OR = 40, OGB_NOT = 41,
+    OGB_OP_COUNT = 42
+};
+#define OGB_MAX_REG 96      /* registers per tape (host compiler enforces)   */
+#define OGB_MAX_FIELD 16383 /* 14-bit operand fields                         */
+
+/* what an output slot of a tape feeds */
+enum ogb_out_kind {
+    OGB_OUT_DYN = 0,        /* node prog: f_a at the node, already scaled by unit_time/unit_state
+                               (reference Dynamics.__call__, optimize.py:1122-1127); row = a   */
+    OGB_OUT_EQ_POINT = 1,   /* node prog: one user equality row per node; row = first row of the
+                               block (relative to the user-equality rows), nodes [glo, ghi)     */
+    OGB_OUT_INEQ_POINT = 2, /* same for user inequality rows                                    */
+    OGB_OUT_RUNNING = 3,    /* node prog: running-cost integrand at the node (optimize.py:706)  */
+    OGB_OUT_EQ_SCALAR = 4,  /* scalar prog: user equality row `row`                             */
+    OGB_OUT_INEQ_SCALAR = 5,/* scalar prog: user inequality row `row`                           */
+    OGB_OUT_COST = 6        /* scalar prog: non-integrated cost (optimize.py:703)               */
+};
+
+typedef struct ogb_out {
+    int32_t kind;
+    int32_t row;
+    int32_t glo, ghi;       /* global node range (over concatenated phases) for *_POINT kinds  */
+} ogb_out;
+
+typedef struct ogb_program {
+    const uint64_t* code_h;   int32_t ncode;
+    const double*   consts_h; int32_t nconsts;
+    const ogb_out*  outs_h;   int32_t nouts;   /* slot i of OGB_OUT <-> outs_h[i] */
+    int32_t nreg;
+} ogb_program;
+
+/* Everything `Problem.__init__` + the unit setters + the traced callbacks define
+ * (reference optimize.py:759-823, :579-639).  All pointers are HOST pointers.      */
+typedef struct ogb_problem_desc {
+    int32_t nsec;                 /* number_of_section                                */
+    const int32_t* nodes_h;       /* [nsec]                                           */
+    const int32_t* nstates_h;     /* [nsec]                                           */
+    const int32_t* ncontrols_h;   /* [nsec]                                           */
+    const double*  unit_states_h; /* unit_states, phases concatenated [sum nstates]   */
+    double unit_time;
+    double t0;                    /* prob.t0 as `time_start(0)` returns it (:343-344) */
+    const uint8_t* knot_smooth_h; /* [nsec-1] knot_states_smooth                      */
+    int32_t meq_user;             /* rows returned by the user equality               */
+    int32_t mineq_user;           /* rows returned by the user inequality             */
+    int32_t has_running_cost;
+    const ogb_program* node_prog_h;   /* [nsec] one node program per phase            */
+    const ogb_program* scalar_prog_h; /* exactly one (may have ncode == 0 outs == 0)  */
+} ogb_problem_desc;
+
+typedef struct ogb_problem_info {
+    int32_t nvars;      /* number_of_variables (optimize.py:781)                      */
+    int32_t meq;        /* user eq rows + collocation defects + knot rows             */
+    int32_t mineq;      /* user inequality rows                                       */
+    int32_t nrows;      /* meq + mineq + 1 (the last row carries cost / grad cost)    */
+    int32_t ndx;        /* doubles of D.X per instance = sum_s nstates_s * nodes_s    */
+    int32_t total_nodes;
+    int32_t tile_cols;  /* Jacobian columns staged per shared-memory tile             */
+    int32_t group_cols; /* Jacobian columns per work item                             */
+    int32_t smem_bytes; /* dynamic shared memory of the sweep kernel                  */
+    int32_t ctas_per_sm;
+} ogb_problem_info;
+
+const char* ogb_last_error(void);
+int ogb_version(void);
+
+/* LGL nodes, weights, differentiation matrix (row-major N x N).
+ * Replaces Problem._nodes_LGL / _weight_LGL / _differentiation_matrix_LGL
+ * (reference optimize.py:183-213).  `ogb_lgl_build` writes DEVICE memory from a
+ * kernel; `ogb_lgl_build_host` runs the same code on the host for the facade's
+ * constructor attributes (prob.tau / w / D / time; optimize.py:786-791).          */
+int ogb_lgl_build(int N, double* tau, double* w, double* D, void* stream);
+int ogb_lgl_build_host(int N, double* tau_h, double* w_h, double* D_h);
+
+/* Problem handle on the current CUDA device.  Replaces the layout tables
+ * (_make_param_division, optimize.py:237-245) and owns D per phase on the device. */
+void* ogb_problem_create(const ogb_problem_desc* desc);
+void  ogb_problem_destroy(void* prob);
+int   ogb_problem_info_get(void* prob, ogb_problem_info* out);
+
+/* Scratch the caller must provide to ogb_eval / ogb_eval_fd for a batch of B.     */
+size_t ogb_workspace_bytes(void* prob, int B);
+
+/* K1: D.X for every phase and state of every instance as a batched FP64
+ * tensor-core GEMM.  Replaces `D[i].dot(state_temp)` (reference optimize.py:680-682).
+ * p [B, nvars] -> DX [B, ndx] (phase-major, then state-major, then node).         */
+int ogb_dx_gemm(void* prob, const double* p, int B, double* DX, void* stream);
+
+/* c = [c_eq ; c_ineq ; cost] at every p[b] (no clipping).  Replaces the
+ * `for_solver(equality_add)`, `for_solver(inequality)` and `for_solver(cost_add)`
+ * closures (reference optimize.py:670-715).  c [B, nrows].                        */
+int ogb_eval(void* prob, const double* p, int B, double* c, void* work, void* stream);
+
+/* One eval per instance: c at x = clip(p[b], lb, ub) and the dense 2-point forward
+ * difference Jacobian of c, bound-adjusted steps, dx = (x+h)-x as divisor.
+ * Replaces SciPy's cjac -> approx_derivative -> _dense_difference on the reference's
+ * closures (scipy/optimize/_slsqp_py.py:353-367, _numdiff.py:14-90,582-600,683-712).
+ * J [B, nvars, nrows]: J[b, j, :] is the column of variable j (contiguous), i.e.
+ * the Fortran-ordered (nrows, nvars) matrix SLSQP consumes.  lb / ub [nvars] use
+ * +-inf for "no bound".                                                           */
+int ogb_eval_fd(void* prob, const double* p, const double* lb, const double* ub,
+                double abs_step, int B, double* c, double* J, void* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGB200_H */

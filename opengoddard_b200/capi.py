@@ -1,0 +1,161 @@
+"""ctypes binding of libogb200.so (include/ogb200.h).  No torch types cross this
+boundary: device buffers are passed as raw addresses (`tensor.data_ptr()`), the
+stream as the raw `cudaStream_t`.
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  If it is
+missing the import of anything that needs it raises -- there is no fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libogb200.so")
+
+
+class OgbOut(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("row", C.c_int32), ("glo", C.c_int32), ("ghi", C.c_int32)]
+
+
+class OgbProgram(C.Structure):
+    _fields_ = [("code_h", C.POINTER(C.c_uint64)), ("ncode", C.c_int32),
+                ("consts_h", C.POINTER(C.c_double)), ("nconsts", C.c_int32),
+                ("outs_h", C.POINTER(OgbOut)), ("nouts", C.c_int32),
+                ("nreg", C.c_int32)]
+
+
+class OgbProblemDesc(C.Structure):
+    _fields_ = [("nsec", C.c_int32),
+                ("nodes_h", C.POINTER(C.c_int32)),
+                ("nstates_h", C.POINTER(C.c_int32)),
+                ("ncontrols_h", C.POINTER(C.c_int32)),
+                ("unit_states_h", C.POINTER(C.c_double)),
+                ("unit_time", C.c_double),
+                ("t0", C.c_double),
+                ("knot_smooth_h", C.POINTER(C.c_uint8)),
+                ("meq_user", C.c_int32),
+                ("mineq_user", C.c_int32),
+                ("has_running_cost", C.c_int32),
+                ("node_prog_h", C.POINTER(OgbProgram)),
+                ("scalar_prog_h", C.POINTER(OgbProgram))]
+
+
+class OgbProblemInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nvars", "meq", "mineq", "nrows", "ndx", "total_nodes",
+                                          "tile_cols", "group_cols", "smem_bytes", "ctas_per_sm")]
+
+
+class OgbError(RuntimeError):
+    pass
+
+
+def _program(tape, keep):
+    code = np.ascontiguousarray(tape.code, dtype=np.uint64)
+    consts = np.ascontiguousarray(tape.consts if len(tape.consts) else np.zeros(1), dtype=np.float64)
+    outs = (OgbOut * max(1, len(tape.outs)))()
+    for i, (kind, row, glo, ghi) in enumerate(tape.outs):
+        outs[i] = OgbOut(kind, row, glo, ghi)
+    keep.extend([code, consts, outs])
+    return OgbProgram(code.ctypes.data_as(C.POINTER(C.c_uint64)), len(code),
+                      consts.ctypes.data_as(C.POINTER(C.c_double)), len(tape.consts),
+                      outs, len(tape.outs), tape.nreg)
+
+
+def make_desc(ir):
+    """ProblemIR (tape.py) -> (OgbProblemDesc, keepalive list)."""
+    keep = []
+
+    def arr(values, ctype, dtype):
+        a = np.ascontiguousarray(values if len(values) else [0], dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(ctype))
+
+    progs = (OgbProgram * len(ir.node_tapes))(*[_program(t, keep) for t in ir.node_tapes])
+    scalar = (OgbProgram * 1)(_program(ir.scalar_tape, keep))
+    keep.extend([progs, scalar])
+    desc = OgbProblemDesc(
+        len(ir.nodes), arr(ir.nodes, C.c_int32, np.int32), arr(ir.nstates, C.c_int32, np.int32),
+        arr(ir.ncontrols, C.c_int32, np.int32), arr(ir.unit_states, C.c_double, np.float64),
+        float(ir.unit_time), float(ir.t0),
+        arr([1 if k else 0 for k in ir.knot_smooth], C.c_uint8, np.uint8),
+        int(ir.meq_user), int(ir.mineq_user), 1 if ir.has_running_cost else 0, progs, scalar)
+    return desc, keep
+
+
+class Binding:
+    """Typed access to the entry points of a library exporting `<prefix>*` symbols."""
+
+    def __init__(self, path, prefix="ogb_"):
+        if not os.path.isfile(path):
+            raise OgbError("%s not found -- build it with `python __graft_entry__.py build` "
+                           "(nvcc, sm_100a); OpenGoddard-B200 has no CPU fallback" % path)
+        self.path, self.prefix = path, prefix
+        self.lib = C.CDLL(path)
+        f = lambda n: getattr(self.lib, prefix + n)
+        self.last_error = f("last_error")
+        self.last_error.restype = C.c_char_p
+        self.problem_create = f("problem_create")
+        self.problem_create.restype = C.c_void_p
+        self.problem_create.argtypes = [C.POINTER(OgbProblemDesc)]
+        self.problem_destroy = f("problem_destroy")
+        self.problem_destroy.restype = None
+        self.problem_destroy.argtypes = [C.c_void_p]
+        self.problem_info_get = f("problem_info_get")
+        self.problem_info_get.restype = C.c_int
+        self.problem_info_get.argtypes = [C.c_void_p, C.POINTER(OgbProblemInfo)]
+
+    def error(self):
+        msg = self.last_error()
+        return msg.decode() if msg else ""
+
+    def create(self, ir):
+        desc, keep = make_desc(ir)
+        h = self.problem_create(C.byref(desc))
+        if not h:
+            raise OgbError("ogb_problem_create failed: " + self.error())
+        info = OgbProblemInfo()
+        self.problem_info_get(h, C.byref(info))
+        return h, info
+
+
+_ogb = None
+
+
+def ogb():
+    """The product library (singleton).  Raises OgbError if it has not been built."""
+    global _ogb
+    if _ogb is None:
+        b = Binding(LIB_PATH, "ogb_")
+        L = b.lib
+        vp, dp, i32 = C.c_void_p, C.c_void_p, C.c_int
+        L.ogb_version.restype = C.c_int
+        L.ogb_lgl_build.restype = C.c_int
+        L.ogb_lgl_build.argtypes = [i32, dp, dp, dp, vp]
+        L.ogb_lgl_build_host.restype = C.c_int
+        L.ogb_lgl_build_host.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double)]
+        L.ogb_workspace_bytes.restype = C.c_size_t
+        L.ogb_workspace_bytes.argtypes = [vp, i32]
+        L.ogb_dx_gemm.restype = C.c_int
+        L.ogb_dx_gemm.argtypes = [vp, dp, i32, dp, vp]
+        L.ogb_eval.restype = C.c_int
+        L.ogb_eval.argtypes = [vp, dp, i32, dp, vp, vp]
+        L.ogb_eval_fd.restype = C.c_int
+        L.ogb_eval_fd.argtypes = [vp, dp, dp, dp, C.c_double, i32, dp, dp, vp, vp]
+        _ogb = b
+    return _ogb
+
+
+def lgl_host(N):
+    """tau, w, D of the N-point LGL rule, computed by libogb200's host entry point (the
+    same __host__ __device__ code the device kernel runs)."""
+    b = ogb()
+    tau = np.empty(N)
+    w = np.empty(N)
+    D = np.empty((N, N))
+    ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = b.lib.ogb_lgl_build_host(int(N), ptr(tau), ptr(w), ptr(D))
+    if rc != 0:
+        raise OgbError("ogb_lgl_build_host failed: " + b.error())
+    return tau, w, D

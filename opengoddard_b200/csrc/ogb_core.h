@@ -1,0 +1,445 @@
+// ogb_core.h -- the arithmetic of the hot path, shared by every kernel.
+//
+// Everything here is `__host__ __device__`: the CUDA kernels in ogb_kernels.cu call
+// these functions with (threadIdx, blockDim) striding; tests/emu/ compiles the same
+// header with g++ and calls them serially, so index arithmetic and row assembly can
+// be checked against the golden vectors in the GPU-less build container.  The
+// product library never runs this code on the host except ogb_lgl_build_host.
+//
+// Reference being replaced (file:line = /root/reference/OpenGoddard/optimize.py):
+//   LGL basis :183-213, accessors :271-360, equality_add :670-698, cost_add :700-709,
+//   Dynamics.__call__ :1122-1127, Condition :1012-1066; SciPy FD stepping
+//   scipy/optimize/_numdiff.py:14-90,582-600,683-712.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "ogb200.h"
+
+#if defined(__CUDACC__)
+#define OGB_HD __host__ __device__ __forceinline__
+#else
+#define OGB_HD inline
+#endif
+
+// ------------------------------------------------------------------ device-side POD
+struct OgbSec {
+    int N, ns, nc, nb;      // nodes, states, controls, blocks (= ns + nc)
+    int off;                // first variable of the phase in p
+    int g0;                 // global node offset (phases concatenated)
+    int rdef;               // first collocation-defect row of the phase in c
+    int dxoff;              // offset of the phase in the D.X scratch (ns * N doubles)
+    int doff;               // offset of the phase's D / D^T (N * N doubles)
+    int tf_idx;             // variable index of the phase's final time
+    int t0_idx;             // variable index of the phase's start time, -1 = constant t0
+    int us_off;             // offset into the concatenated unit_states
+    int code_off, ncode, const_off, out_off, nouts, nreg;   // node program
+    int run_slot;           // output slot carrying the running-cost integrand, -1 = none
+    int pad;
+};
+
+struct OgbKnot {            // one smooth-state knot row (optimize.py:689-696)
+    int row, var_prev, var_post, pad;
+    double u_prev, u_post;  // unit_states[knot][a], unit_states[knot+1][a]
+};
+
+struct OgbCol {             // how Jacobian column j is produced
+    int sec;                // phase of a state/control variable; -1 = final-time variable
+    int blk;                // block (state or control number) -- or the phase whose t_f it is
+    int k;                  // node within the phase
+    int pick;               // index into the scalar program's pick list, -1 = not picked
+};
+
+struct OgbProb {
+    int nsec, n, M, meq, mineq, ndx, gtot, nknot, npick, has_running, max_nouts;
+    int sc_code_off, sc_ncode, sc_const_off, sc_out_off, sc_nouts, sc_nreg, sc_cost_slot;
+    double unit_time, t0x;  // t0x = time_start(0) / unit_time (optimize.py:683)
+    const OgbSec* sec;
+    const ogb_out* outs;    // rows already absolute
+    const uint64_t* code;
+    const double* consts;
+    const double* D;        // row-major per phase
+    const double* Dt;       // transposed per phase
+    const double* w;        // LGL weights, phases concatenated
+    const double* ustate;
+    const OgbKnot* knots;
+    const OgbCol* cols;
+    const int* pickvars;
+};
+
+struct OgbWork {            // per work item scratch (shared memory on the device)
+    double* sp;             // [n]     decision vector (clipped when differencing)
+    double* sdx;            // [ndx]   D.X at the base point
+    double* sbase;          // [max_nouts][gtot] node-program outputs at the base point
+    double* sc;             // [M]     c at the base point
+    double* scbase;         // [sc_nouts] scalar-program outputs at the base point
+    double* coef;           // [3*nsec] (tfx - tix)/2, tfx, tix per phase
+    double* prefix;         // [gtot+1] left-to-right partial sums of the running cost
+    double* pert;           // [max_nouts][G] node-program outputs, one perturbed column each
+    double* pdx;            // [G] dx = (x0 + h) - x0
+    double* px1;            // [G] x0 + h
+    double* scpert;         // [sc_nouts][npick] scalar-program outputs per perturbed pick
+    double* pdlt;           // [G] change of the non-dimensional state operand of D.X (0 for controls / times)
+    OgbCol* pcol;           // [G] production record of each column of the work item
+    int G;
+};
+
+// ------------------------------------------------------------------ LGL basis
+// P_n and P_n' by the three-term recurrence.
+OGB_HD void ogb_legendre(int n, double x, double* P, double* dP) {
+    double p0 = 1.0, p1 = x, d0 = 0.0, d1 = 1.0;
+    if (n == 0) { *P = 1.0; *dP = 0.0; return; }
+    for (int k = 2; k <= n; ++k) {
+        double pk = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+        double dk = d0 + (2.0 * k - 1.0) * p1;
+        p0 = p1; p1 = pk; d0 = d1; d1 = dk;
+    }
+    *P = p1; *dP = d1;
+}
+
+// i-th LGL node of an N-point rule: -1, the roots of P'_{N-1}, +1 (optimize.py:183-187).
+// Newton on q = P'_{N-1} with q' from Legendre's equation, started from the
+// Chebyshev-Gauss-Lobatto point.
+OGB_HD double ogb_lgl_node(int N, int i) {
+    if (i == 0) return -1.0;
+    if (i == N - 1) return 1.0;
+    const int n = N - 1;
+    if (2 * i == n) return 0.0;
+    double x = -cos(3.14159265358979323846 * (double)i / (double)n);
+    for (int it = 0; it < 100; ++it) {
+        double P, dP;
+        ogb_legendre(n, x, &P, &dP);
+        double ddP = (2.0 * x * dP - (double)n * (n + 1.0) * P) / (1.0 - x * x);
+        double step = dP / ddP;
+        x -= step;
+        if (fabs(step) <= 1e-16 * fabs(x)) break;
+    }
+    return x;
+}
+
+// w_i = 2 / (N (N-1) P_{N-1}(tau_i)^2)   (optimize.py:189-195)
+OGB_HD double ogb_lgl_weight(int N, double tau_i) {
+    double P, dP;
+    ogb_legendre(N - 1, tau_i, &P, &dP);
+    return 2.0 / ((double)N * (N - 1.0) * (P * P));
+}
+
+// D_ij (optimize.py:197-213); Pi, Pj = P_{N-1}(tau_i), P_{N-1}(tau_j)
+OGB_HD double ogb_lgl_dij(int N, int i, int j, double ti, double tj, double Pi, double Pj) {
+    if (i != j) return Pi / Pj / (ti - tj);
+    if (i == 0) return -(double)N * (N - 1.0) * 0.25;
+    if (i == N - 1) return (double)N * (N - 1.0) * 0.25;
+    return 0.0;
+}
+
+// ------------------------------------------------------------------ FD step
+// h for variable x0 exactly as approx_derivative(method='2-point', abs_step, bounds)
+// picks it (scipy/optimize/_numdiff.py:582-600 then :46-71 with num_steps = 1).
+OGB_HD double ogb_fd_step(double x0, double lb, double ub, double abs_step) {
+    double h = abs_step;
+    if ((x0 + h) - x0 == 0.0) {
+        const double sq = 1.4901161193847656e-08;   // EPS**0.5, _eps_for_method
+        h = sq * (x0 >= 0.0 ? 1.0 : -1.0) * fmax(1.0, fabs(x0));
+    }
+    const double lower = x0 - lb, upper = ub - x0;
+    const double x1 = x0 + h;
+    const bool violated = (x1 < lb) || (x1 > ub);
+    const bool fitting = fabs(h) <= fmax(lower, upper);
+    if (violated && fitting) h = -h;
+    if (!fitting) h = (upper >= lower) ? upper : -lower;
+    return h;
+}
+
+// ------------------------------------------------------------------ tape interpreter
+struct OgbNodeLoad {        // node program input: block `a` of the phase at one node
+    const double* at;       // &sp[off + k]
+    int N;
+    int pblk;               // perturbed block, -1 = none
+    double x1;
+    OGB_HD double operator()(int a) const { return a == pblk ? x1 : at[a * N]; }
+};
+
+struct OgbScalarLoad {      // scalar program input: variable `a` of p
+    const double* sp;
+    int pvar;               // perturbed variable, -1 = none
+    double x1;
+    OGB_HD double operator()(int a) const { return a == pvar ? x1 : sp[a]; }
+};
+
+template <class Load>
+OGB_HD void ogb_run_tape(const uint64_t* code, int ncode, const double* consts,
+                         const Load& ld, double* out, int ostride) {
+    double r[OGB_MAX_REG];
+    for (int pc = 0; pc < ncode; ++pc) {
+        const uint64_t ins = code[pc];
+        const int op = (int)(ins >> 56);
+        const int d = (int)((ins >> 42) & 0x3fff);
+        const int a = (int)((ins >> 28) & 0x3fff);
+        const int b = (int)((ins >> 14) & 0x3fff);
+        const int c = (int)(ins & 0x3fff);
+        double v;
+        switch (op) {
+            case OGB_LDP: v = ld(a); break;
+            case OGB_LDC: v = consts[a]; break;
+            case OGB_OUT: out[d * ostride] = r[a]; continue;
+            case OGB_ADD: v = r[a] + r[b]; break;
+            case OGB_SUB: v = r[a] - r[b]; break;
+            case OGB_MUL: v = r[a] * r[b]; break;
+            case OGB_DIV: v = r[a] / r[b]; break;
+            case OGB_POW: v = pow(r[a], r[b]); break;
+            case OGB_MIN: v = fmin(r[a], r[b]); break;
+            case OGB_MAX: v = fmax(r[a], r[b]); break;
+            case OGB_ATAN2: v = atan2(r[a], r[b]); break;
+            case OGB_LT: v = r[a] < r[b] ? 1.0 : 0.0; break;
+            case OGB_LE: v = r[a] <= r[b] ? 1.0 : 0.0; break;
+            case OGB_GT: v = r[a] > r[b] ? 1.0 : 0.0; break;
+            case OGB_GE: v = r[a] >= r[b] ? 1.0 : 0.0; break;
+            case OGB_EQ: v = r[a] == r[b] ? 1.0 : 0.0; break;
+            case OGB_NE: v = r[a] != r[b] ? 1.0 : 0.0; break;
+            case OGB_SEL: v = r[a] != 0.0 ? r[b] : r[c]; break;
+            case OGB_NEG: v = -r[a]; break;
+            case OGB_SQRT: v = sqrt(r[a]); break;
+            case OGB_EXP: v = exp(r[a]); break;
+            case OGB_LOG: v = log(r[a]); break;
+            case OGB_SIN: v = sin(r[a]); break;
+            case OGB_COS: v = cos(r[a]); break;
+            case OGB_TAN: v = tan(r[a]); break;
+            case OGB_ABS: v = fabs(r[a]); break;
+            case OGB_SQUARE: v = r[a] * r[a]; break;
+            case OGB_RECIP: v = 1.0 / r[a]; break;
+            case OGB_ASIN: v = asin(r[a]); break;
+            case OGB_ACOS: v = acos(r[a]); break;
+            case OGB_ATAN: v = atan(r[a]); break;
+            case OGB_SINH: v = sinh(r[a]); break;
+            case OGB_COSH: v = cosh(r[a]); break;
+            case OGB_TANH: v = tanh(r[a]); break;
+            case OGB_LOG10: v = log10(r[a]); break;
+            case OGB_SIGN: v = (r[a] > 0.0) ? 1.0 : ((r[a] < 0.0) ? -1.0 : r[a]); break;
+            case OGB_FLOOR: v = floor(r[a]); break;
+            case OGB_CEIL: v = ceil(r[a]); break;
+            case OGB_AND: v = (r[a] != 0.0 && r[b] != 0.0) ? 1.0 : 0.0; break;
+            case OGB_OR: v = (r[a] != 0.0 || r[b] != 0.0) ? 1.0 : 0.0; break;
+            case OGB_NOT: v = (r[a] == 0.0) ? 1.0 : 0.0; break;
+            default: continue;
+        }
+        r[d] = v;
+    }
+}
+
+// ------------------------------------------------------------------ helpers
+OGB_HD int ogb_sec_of_node(const OgbProb& P, int g) {
+    int s = 0;
+    while (s + 1 < P.nsec && g >= P.sec[s + 1].g0) ++s;
+    return s;
+}
+
+// state_temp = states(j, i) / unit = (p * unit) / unit   (optimize.py:284 then :681)
+OGB_HD double ogb_nd(double p, double u) { return (p * u) / u; }
+
+// ------------------------------------------------------------------ K1 reference loop
+// D.X for one (instance, phase, state) row; the CUDA path computes the same numbers
+// with FP64 tensor-core MMAs (ogb_kernels.cu), this is the emulation / tail path.
+OGB_HD void ogb_dx_row(const OgbProb& P, const OgbSec& S, int a, const double* p, double* dx) {
+    const double u = P.ustate[S.us_off + a];
+    const double* x = p + S.off + a * S.N;
+    const double* D = P.D + S.doff;
+    for (int i = 0; i < S.N; ++i) {
+        double acc = 0.0;
+        for (int l = 0; l < S.N; ++l) acc += D[i * S.N + l] * ogb_nd(x[l], u);
+        dx[S.dxoff + a * S.N + i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ phase 2: tape jobs
+// Job q of a work item: q < gtot: node program at base node q; q == gtot: scalar program
+// at the base point + the per-phase time coefficients; q > gtot: Jacobian column
+// jlo + (q - gtot - 1): FD step, perturbed node program, perturbed scalar program.
+OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
+                    const double* lb, const double* ub, double abs_step) {
+    if (q < P.gtot) {
+        const OgbSec& S = P.sec[ogb_sec_of_node(P, q)];
+        OgbNodeLoad ld{W.sp + S.off + (q - S.g0), S.N, -1, 0.0};
+        ogb_run_tape(P.code + S.code_off, S.ncode, P.consts + S.const_off, ld,
+                     W.sbase + q, P.gtot);
+    } else if (q == P.gtot) {
+        OgbScalarLoad ld{W.sp, -1, 0.0};
+        ogb_run_tape(P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, ld,
+                     W.scbase, 1);
+        for (int s = 0; s < P.nsec; ++s) {
+            const OgbSec& S = P.sec[s];
+            const double tfx = ogb_nd(W.sp[S.tf_idx], P.unit_time);                 // :684
+            const double tix = S.t0_idx < 0 ? P.t0x : ogb_nd(W.sp[S.t0_idx], P.unit_time);  // :683
+            W.coef[3 * s + 0] = (tfx - tix) / 2.0;                                  // :686
+            W.coef[3 * s + 1] = tfx;
+            W.coef[3 * s + 2] = tix;
+        }
+    } else {
+        const int cl = q - P.gtot - 1;
+        const int j = jlo + cl;
+        const double x0 = W.sp[j];
+        const double h = ogb_fd_step(x0, lb[j], ub[j], abs_step);
+        const double x1 = x0 + h;                     // _numdiff.py:701
+        W.px1[cl] = x1;
+        W.pdx[cl] = x1 - x0;                          // _numdiff.py:707
+        const OgbCol col = P.cols[j];
+        W.pcol[cl] = col;
+        double dlt = 0.0;
+        if (col.sec >= 0) {
+            const OgbSec& S = P.sec[col.sec];
+            if (col.blk < S.ns) {
+                const double u = P.ustate[S.us_off + col.blk];
+                dlt = ogb_nd(x1, u) - ogb_nd(x0, u);
+            }
+            OgbNodeLoad ld{W.sp + S.off + col.k, S.N, col.blk, x1};
+            ogb_run_tape(P.code + S.code_off, S.ncode, P.consts + S.const_off, ld,
+                         W.pert + cl, W.G);
+        }
+        W.pdlt[cl] = dlt;
+        if (col.pick >= 0) {
+            OgbScalarLoad ld{W.sp, j, x1};
+            ogb_run_tape(P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, ld,
+                         W.scpert + col.pick, P.npick);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ phase 3: c at the base point
+OGB_HD void ogb_assemble_base(const OgbProb& P, const OgbWork& W, int tid, int nthr) {
+    // collocation defects  D.x - (tf - t0)/2 * f   (optimize.py:686)
+    for (int s = 0; s < P.nsec; ++s) {
+        const OgbSec& S = P.sec[s];
+        const double coef = W.coef[3 * s];
+        for (int e = tid; e < S.ns * S.N; e += nthr) {
+            const int a = e / S.N, i = e - a * S.N;
+            W.sc[S.rdef + e] = W.sdx[S.dxoff + e] - coef * W.sbase[a * P.gtot + S.g0 + i];
+        }
+        // user rows that are pointwise in the node
+        for (int slot = S.ns; slot < S.nouts; ++slot) {
+            const ogb_out o = P.outs[S.out_off + slot];
+            if (o.kind != OGB_OUT_EQ_POINT && o.kind != OGB_OUT_INEQ_POINT) continue;
+            for (int k = tid; k < S.N; k += nthr) {
+                const int g = S.g0 + k;
+                if (g >= o.glo && g < o.ghi) W.sc[o.row + (g - o.glo)] = W.sbase[slot * P.gtot + g];
+            }
+        }
+    }
+    // knot rows (optimize.py:689-696; `post` is divided by the PREVIOUS phase's unit)
+    for (int t = tid; t < P.nknot; t += nthr) {
+        const OgbKnot K = P.knots[t];
+        W.sc[K.row] = ogb_nd(W.sp[K.var_prev], K.u_prev) - (W.sp[K.var_post] * K.u_post) / K.u_prev;
+    }
+    // scalar user rows
+    for (int slot = tid; slot < P.sc_nouts; slot += nthr) {
+        const ogb_out o = P.outs[P.sc_out_off + slot];
+        if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR) W.sc[o.row] = W.scbase[slot];
+    }
+    // cost = cost() + sum(running * w), summed left to right (optimize.py:700-709)
+    if (tid == 0) {
+        double cost = W.scbase[P.sc_cost_slot];
+        if (P.has_running) {
+            double acc = 0.0;
+            for (int g = 0; g < P.gtot; ++g) {
+                W.prefix[g] = acc;
+                const OgbSec& S = P.sec[ogb_sec_of_node(P, g)];
+                acc += W.sbase[S.run_slot * P.gtot + g] * P.w[g];
+            }
+            W.prefix[P.gtot] = acc;
+            cost = cost + acc;
+        }
+        W.sc[P.M - 1] = cost;
+    }
+}
+
+// ------------------------------------------------------------------ phase 4: one Jacobian column
+// Fills the non-zeros of column j into `col` (M doubles, pre-zeroed):
+//     col[r] = (c_r(x + h e_j) - c_r(x)) / dx          (_numdiff.py:708-711)
+// recomputing only the rows that can change.  `lane` / `nlanes` stride the work.
+OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl, double* col,
+                               int lane, int nlanes) {
+    const OgbCol cd = W.pcol[cl];
+    const double dx = W.pdx[cl];
+    const double x1 = W.px1[cl];
+    const int gt = P.gtot;
+    if (cd.sec >= 0) {
+        const OgbSec& S = P.sec[cd.sec];
+        const int k = cd.k, g = S.g0 + k, N = S.N;
+        const double coef = W.coef[3 * cd.sec];
+        const double dlt = W.pdlt[cl];
+        int a = -1;
+        if (cd.blk < S.ns) {                                   // a state: D.x moves in every node row
+            a = cd.blk;
+            const double* Dt = P.Dt + S.doff + k * N;          // column k of D
+            for (int i = lane; i < N; i += nlanes) {
+                if (i == k) continue;
+                const int e = a * N + i;
+                const double cp = (W.sdx[S.dxoff + e] + Dt[i] * dlt) - coef * W.sbase[a * gt + S.g0 + i];
+                col[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
+            }
+        }
+        for (int b = lane; b < S.ns; b += nlanes) {            // dynamics moved at node k only
+            const int e = b * N + k;
+            double dxp = W.sdx[S.dxoff + e];
+            if (b == a) dxp = dxp + P.D[S.doff + k * N + k] * dlt;
+            const double cp = dxp - coef * W.pert[b * W.G + cl];
+            col[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
+        }
+        for (int slot = S.ns + lane; slot < S.nouts; slot += nlanes) {
+            const ogb_out o = P.outs[S.out_off + slot];
+            if ((o.kind == OGB_OUT_EQ_POINT || o.kind == OGB_OUT_INEQ_POINT) && g >= o.glo && g < o.ghi) {
+                const int r = o.row + (g - o.glo);
+                col[r] = (W.pert[slot * W.G + cl] - W.sc[r]) / dx;
+            }
+        }
+        for (int t = lane; t < P.nknot; t += nlanes) {
+            const OgbKnot K = P.knots[t];
+            if (K.var_prev == j || K.var_post == j) {
+                const double xp = K.var_prev == j ? x1 : W.sp[K.var_prev];
+                const double xq = K.var_post == j ? x1 : W.sp[K.var_post];
+                const double cp = ogb_nd(xp, K.u_prev) - (xq * K.u_post) / K.u_prev;
+                col[K.row] = (cp - W.sc[K.row]) / dx;
+            }
+        }
+    } else {                                                   // a final time: defects of <= 2 phases rescale
+        const double tfx1 = ogb_nd(x1, P.unit_time);
+        for (int s = cd.blk; s < P.nsec && s <= cd.blk + 1; ++s) {
+            const OgbSec& S = P.sec[s];
+            double coef1;
+            if (s == cd.blk) coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0;
+            else if (S.t0_idx == j) coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0;
+            else continue;
+            for (int e = lane; e < S.ns * S.N; e += nlanes) {
+                const int b = e / S.N, i = e - b * S.N;
+                const double cp = W.sdx[S.dxoff + e] - coef1 * W.sbase[b * gt + S.g0 + i];
+                col[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
+            }
+        }
+    }
+    if (cd.pick >= 0) {                                        // rows of the scalar program
+        for (int slot = lane; slot < P.sc_nouts; slot += nlanes) {
+            const ogb_out o = P.outs[P.sc_out_off + slot];
+            if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR)
+                col[o.row] = (W.scpert[slot * P.npick + cd.pick] - W.sc[o.row]) / dx;
+        }
+    }
+    if (lane == 0) {                                           // cost row (the "+1" row)
+        const bool run = P.has_running && cd.sec >= 0 && P.sec[cd.sec].run_slot >= 0;
+        if (cd.pick >= 0 || run) {
+            double cost = cd.pick >= 0 ? W.scpert[P.sc_cost_slot * P.npick + cd.pick]
+                                       : W.scbase[P.sc_cost_slot];
+            if (P.has_running) {
+                double acc = W.prefix[gt];
+                if (run) {
+                    const OgbSec& S = P.sec[cd.sec];
+                    const int g = S.g0 + cd.k;
+                    acc = W.prefix[g] + W.pert[S.run_slot * W.G + cl] * P.w[g];
+                    for (int g2 = g + 1; g2 < gt; ++g2) {
+                        const OgbSec& S2 = P.sec[ogb_sec_of_node(P, g2)];
+                        acc += W.sbase[S2.run_slot * gt + g2] * P.w[g2];
+                    }
+                }
+                cost = cost + acc;
+            }
+            col[P.M - 1] = (cost - W.sc[P.M - 1]) / dx;
+        }
+    }
+}

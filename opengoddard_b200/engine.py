@@ -1,0 +1,171 @@
+"""Device engine: owns the libogb200 problem handle and the PyTorch tensors around it.
+
+PyTorch is plumbing here (device memory, streams, pinned staging buffers); all
+arithmetic happens in the sm_100a kernels behind the C ABI (include/ogb200.h).
+Everything raises if CUDA or the library is unavailable -- there is no CPU fallback.
+"""
+import numpy as np
+
+from . import capi
+
+ABS_STEP = float(np.sqrt(np.finfo(np.float64).eps))     # scipy/optimize/_slsqp_py.py:34
+
+
+class DeviceProblem:
+    """One traced problem resident on one GPU.
+
+    eval(P)    -> c  (B, nrows)                     reference closures, optimize.py:670-715
+    eval_fd(P) -> c, J (B, nvars, nrows)            + SciPy's FD Jacobian (_numdiff.py:683-712)
+    J[b, j, :] is the column of variable j; rows are [c_eq ; c_ineq ; cost].
+    """
+
+    def __init__(self, ir, bounds, device=None):
+        import torch
+        self.torch = torch
+        self.b = capi.ogb()                       # raises OgbError if the .so is missing
+        if not torch.cuda.is_available():
+            raise capi.OgbError("OpenGoddard-B200 needs a CUDA device (sm_100a); none is "
+                                "visible and there is no CPU fallback for the hot path")
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise capi.OgbError("device must be a CUDA device, not %r" % (self.device,))
+        self.ir = ir
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)    # make sure the context exists
+            self.h, info = self.b.create(ir)
+        self.info = info
+        self.nvars, self.meq, self.mineq, self.nrows = info.nvars, info.meq, info.mineq, info.nrows
+        self.ndx = info.ndx
+        lb, ub = bounds
+        assert len(lb) == self.nvars and len(ub) == self.nvars
+        self.lb = torch.as_tensor(np.asarray(lb, dtype=np.float64), device=self.device)
+        self.ub = torch.as_tensor(np.asarray(ub, dtype=np.float64), device=self.device)
+        self._work = None
+        self._one = None
+        self.launches = 0                         # kernels launched through this handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.b.problem_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _workspace(self, B):
+        need = self.b.lib.ogb_workspace_bytes(self.h, int(B))
+        if self._work is None or self._work.numel() < need:
+            self._work = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        return self._work
+
+    def _check_P(self, P):
+        t = self.torch
+        if not isinstance(P, t.Tensor):
+            P = t.as_tensor(np.ascontiguousarray(P, dtype=np.float64), device=self.device)
+        if P.dim() == 1:
+            P = P.unsqueeze(0)
+        if P.dtype != t.float64 or P.device != self.device or not P.is_contiguous():
+            P = P.to(device=self.device, dtype=t.float64).contiguous()
+        if P.shape[1] != self.nvars:
+            raise ValueError("P must be (B, %d), got %s" % (self.nvars, tuple(P.shape)))
+        return P
+
+    def _rc(self, rc, what):
+        if rc != 0:
+            raise capi.OgbError("%s failed: %s" % (what, self.b.error()))
+
+    # ------------------------------------------------------------------ device API
+    def dx_gemm(self, P, out=None):
+        """K1 alone: D.X for every phase/state of every instance -> (B, ndx)."""
+        t = self.torch
+        P = self._check_P(P)
+        B = P.shape[0]
+        DX = out if out is not None else t.empty((B, self.ndx), dtype=t.float64, device=self.device)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_dx_gemm(self.h, P.data_ptr(), B, DX.data_ptr(), self._stream()),
+                     "ogb_dx_gemm")
+        self.launches += 1
+        return DX
+
+    def eval(self, P, out=None):
+        t = self.torch
+        P = self._check_P(P)
+        B = P.shape[0]
+        c = out if out is not None else t.empty((B, self.nrows), dtype=t.float64, device=self.device)
+        work = self._workspace(B)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_eval(self.h, P.data_ptr(), B, c.data_ptr(), work.data_ptr(),
+                                         self._stream()), "ogb_eval")
+        self.launches += 2
+        return c
+
+    def eval_fd(self, P, out_c=None, out_J=None, abs_step=ABS_STEP):
+        t = self.torch
+        P = self._check_P(P)
+        B = P.shape[0]
+        c = out_c if out_c is not None else t.empty((B, self.nrows), dtype=t.float64, device=self.device)
+        J = out_J if out_J is not None else t.empty((B, self.nvars, self.nrows), dtype=t.float64,
+                                                    device=self.device)
+        assert c.is_contiguous() and J.is_contiguous()
+        work = self._workspace(B)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_eval_fd(self.h, P.data_ptr(), self.lb.data_ptr(), self.ub.data_ptr(),
+                                            float(abs_step), B, c.data_ptr(), J.data_ptr(),
+                                            work.data_ptr(), self._stream()), "ogb_eval_fd")
+        self.launches += 2
+        return c, J
+
+    # ------------------------------------------------------------------ single-instance host API
+    # (what Problem.solve hands to SciPy: host vector in, host arrays out, pinned staging)
+    def _staging(self):
+        if self._one is None:
+            t = self.torch
+            self._one = dict(
+                hx=t.empty((1, self.nvars), dtype=t.float64).pin_memory(),
+                hc=t.empty((1, self.nrows), dtype=t.float64).pin_memory(),
+                hJ=t.empty((1, self.nvars, self.nrows), dtype=t.float64).pin_memory(),
+                dx=t.empty((1, self.nvars), dtype=t.float64, device=self.device),
+                dc=t.empty((1, self.nrows), dtype=t.float64, device=self.device),
+                dJ=t.empty((1, self.nvars, self.nrows), dtype=t.float64, device=self.device))
+        return self._one
+
+    def eval_host(self, x):
+        s = self._staging()
+        s["hx"].numpy()[0, :] = x
+        s["dx"].copy_(s["hx"], non_blocking=True)
+        self.eval(s["dx"], out=s["dc"])
+        s["hc"].copy_(s["dc"], non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return s["hc"].numpy()[0].copy()
+
+    def eval_fd_host(self, x):
+        s = self._staging()
+        s["hx"].numpy()[0, :] = x
+        s["dx"].copy_(s["hx"], non_blocking=True)
+        self.eval_fd(s["dx"], out_c=s["dc"], out_J=s["dJ"])
+        s["hc"].copy_(s["dc"], non_blocking=True)
+        s["hJ"].copy_(s["dJ"], non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return s["hc"].numpy()[0].copy(), s["hJ"].numpy()[0].copy()
+
+
+def lgl_device(N, device="cuda:0"):
+    """K0 on the device: tau (N,), w (N,), D (N, N) as CUDA tensors."""
+    import torch
+    b = capi.ogb()
+    if not torch.cuda.is_available():
+        raise capi.OgbError("ogb_lgl_build needs a CUDA device")
+    dev = torch.device(device)
+    tau = torch.empty(N, dtype=torch.float64, device=dev)
+    w = torch.empty(N, dtype=torch.float64, device=dev)
+    D = torch.empty((N, N), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = b.lib.ogb_lgl_build(int(N), tau.data_ptr(), w.data_ptr(), D.data_ptr(),
+                                 torch.cuda.current_stream(dev).cuda_stream)
+    if rc != 0:
+        raise capi.OgbError("ogb_lgl_build failed: " + b.error())
+    return tau, w, D

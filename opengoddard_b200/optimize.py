@@ -1,0 +1,573 @@
+"""Drop-in facade: ``from OpenGoddard.optimize import Problem, Guess, Condition, Dynamics``.
+
+Same public names, argument meaning, attribute set and error behaviour as the
+reference module (/root/reference/OpenGoddard/optimize.py -- cited per method), so the
+shipped example scripts run unchanged, but the per-SQP-iteration hot path
+(constraint vector + dense forward-difference Jacobian, reference :670-715 driven by
+scipy/optimize/_slsqp_py.py:353-367) is not evaluated in Python: `solve` traces the user
+callbacks once (trace.py), lowers them to device tapes (tape.py) and hands SciPy's
+SLSQP `fun` / `jac` callables that resolve to the sm_100a kernels of libogb200.so
+(engine.py).  New, batched entry points: `Problem.compile`, `Problem.evaluate_batch`.
+
+Backends: "cuda" (default; raises if the library or a GPU is missing -- there is no
+silent fallback) and "host", an explicit opt-in (``prob.backend = "host"`` or
+``OGB200_BACKEND=host``) that evaluates the callbacks eagerly in numpy exactly like
+the reference does; it exists for BASELINE.json's configs[0] (a single CPU instance,
+"plumbing, no GPU") and is never used by the batched hot-path API.
+"""
+import os
+
+import numpy as np
+from scipy import interpolate
+from scipy import optimize
+
+from . import trace as _T
+
+__all__ = ["Problem", "Guess", "Condition", "Dynamics"]
+
+
+def _plt():
+    import matplotlib.pyplot as plt
+    return plt
+
+
+class Problem:
+    """OpenGoddard Problem (reference optimize.py:38-880).
+
+    Args:
+        time_init (list of float): [t_start, t_knot..., t_final]
+        nodes (list of int): LGL nodes per phase
+        number_of_states (list of int), number_of_controls (list of int)
+        maxIterator (int): outer restarts of SLSQP in `solve`
+        method: ignored, as in the reference (only LGL is wired, :787-789)
+    """
+
+    def __init__(self, time_init, nodes, number_of_states, number_of_controls,
+                 maxIterator=100, method="LGL"):
+        assert isinstance(time_init, list), \
+            "error: time_init is not list"
+        assert isinstance(nodes, list), \
+            "error: nodes are not list"
+        assert isinstance(number_of_states, list), \
+            "error: number of states are not list"
+        assert isinstance(number_of_controls, list), \
+            "error: number of controls are not list"
+        assert len(time_init) == len(nodes) + 1, \
+            "error: time_init length is not match nodes length"
+        assert len(nodes) == len(number_of_states), \
+            "error: nodes length is not match states length"
+        assert len(nodes) == len(number_of_controls), \
+            "error: nodes length is not match controls length"
+        from . import capi
+        self.nodes = nodes
+        self.number_of_states = number_of_states
+        self.number_of_controls = number_of_controls
+        self.number_of_section = len(nodes)
+        # end offset of every block, phase by phase (reference :237-245)
+        self.div = []
+        end = 0
+        for N, ns, nc in zip(nodes, number_of_states, number_of_controls):
+            self.div.append([end + N * (k + 1) for k in range(ns + nc)])
+            end = self.div[-1][-1]
+        self.number_of_param = np.array(number_of_states) + np.array(number_of_controls)
+        self.number_of_variables = int(sum(self.number_of_param * nodes)) + self.number_of_section
+        self.tau, self.w, self.D, self.time = [], [], [], []
+        for i, N in enumerate(nodes):
+            tau, w, D = capi.lgl_host(N)          # same code the device kernel runs
+            self.tau.append(tau)
+            self.w.append(w)
+            self.D.append(D)
+            self.time.append((time_init[i + 1] - time_init[i]) / 2.0 * tau
+                             + (time_init[i + 1] + time_init[i]) / 2.0)
+        self.maxIterator = maxIterator
+        self.iterator = 0
+        self.time_init = time_init
+        self.t0 = time_init[0]
+        self.time_all_section = np.concatenate([t for t in self.time])
+        self.unit_states = [[1.0] * ns for ns in number_of_states]
+        self.unit_controls = [[1.0] * nc for nc in number_of_controls]
+        self.unit_time = 1.0
+        self.p = np.zeros(self.number_of_variables, dtype=float)
+        self.bounds = [(None, None)] * self.number_of_variables
+        for s in range(self.number_of_section):
+            self.set_time_final_bounds(s, 0.0, None)
+        self.dynamics = []
+        self.knot_states_smooth = []
+        self.cost = None
+        self.running_cost = None
+        self.cost_derivative = None
+        self.equality = None
+        self.inequality = None
+        for s in range(self.number_of_section):
+            self.set_time_final(s, time_init[s + 1])
+            self.dynamics.append(None)
+        for s in range(self.number_of_section - 1):
+            self.knot_states_smooth.append(True)
+        # ---- B200 engine state (not in the reference)
+        self.backend = None          # None -> $OGB200_BACKEND -> "cuda"
+        self.device = None           # torch device for the cuda backend (default cuda:0)
+        self._engine = None
+
+    # ------------------------------------------------------------------ layout
+    def _span_state(self, state, section):
+        # reference :247-260 (python negative indices are deliberately not normalised:
+        # states(-1, s) addresses the LAST block of the phase)
+        assert section < len(self.nodes), \
+            "section argument out of own section range"
+        assert state < self.number_of_states[section], \
+            "states argument out of own states range"
+        if state == 0:
+            lo = 0 if section == 0 else self.div[section - 1][-1]
+        else:
+            lo = self.div[section][state - 1]
+        return lo, self.div[section][state]
+
+    def _span_control(self, control, section):
+        # reference :262-269
+        assert section < len(self.nodes), \
+            "section argument out of own section range"
+        assert control < self.number_of_controls[section], \
+            "controls argument out of own controls range"
+        k = self.number_of_states[section] + control
+        return self.div[section][k - 1], self.div[section][k]
+
+    def _division_states(self, state, section):
+        lo, hi = self._span_state(state, section)
+        return hi, lo
+
+    def _division_controls(self, control, section):
+        lo, hi = self._span_control(control, section)
+        return hi, lo
+
+    # ------------------------------------------------------------------ getters (:271-375)
+    def states(self, state, section):
+        """dimensional values of one state over the nodes of one phase"""
+        lo, hi = self._span_state(state, section)
+        return self.p[lo:hi] * self.unit_states[section][state]
+
+    def states_all_section(self, state):
+        out = np.zeros(0)
+        for s in range(self.number_of_section):
+            out = np.concatenate([out, self.states(state, s)])
+        return out
+
+    def controls(self, control, section):
+        lo, hi = self._span_control(control, section)
+        return self.p[lo:hi] * self.unit_controls[section][control]
+
+    def controls_all_section(self, control):
+        out = np.zeros(0)
+        for s in range(self.number_of_section):
+            out = np.concatenate([out, self.controls(control, s)])
+        return out
+
+    def time_start(self, section):
+        if section == 0:
+            return self.t0
+        return self.p[range(-self.number_of_section - 1, 0)[section]] * self.unit_time
+
+    def time_final(self, section):
+        return self.p[range(-self.number_of_section, 0)[section]] * self.unit_time
+
+    def time_final_all_section(self):
+        return [self.time_final(s) for s in range(self.number_of_section)]
+
+    # ------------------------------------------------------------------ setters (:377-440)
+    def set_states(self, state, section, value):
+        assert len(value) == self.nodes[section], "Error: value length is NOT match nodes length"
+        lo, hi = self._span_state(state, section)
+        self.p[lo:hi] = value / self.unit_states[section][state]
+
+    def set_states_all_section(self, state, value_all_section):
+        at = 0
+        for s in range(self.number_of_section):
+            self.set_states(state, s, value_all_section[at:at + self.nodes[s]])
+            at += self.nodes[s]
+
+    def set_controls(self, control, section, value):
+        assert len(value) == self.nodes[section], "Error: value length is NOT match nodes length"
+        lo, hi = self._span_control(control, section)
+        self.p[lo:hi] = value / self.unit_controls[section][control]
+
+    def set_controls_all_section(self, control, value_all_section):
+        at = 0
+        for s in range(self.number_of_section):
+            self.set_controls(control, s, value_all_section[at:at + self.nodes[s]])
+            at += self.nodes[s]
+
+    def set_time_final(self, section, value):
+        self.p[range(-self.number_of_section, 0)[section]] = value / self.unit_time
+
+    # ------------------------------------------------------------------ bounds (:442-507)
+    def set_states_bounds(self, state, section, lb, ub):
+        u = self.unit_states[section][state]
+        lb = lb / u if lb is not None else None
+        ub = ub / u if ub is not None else None
+        lo, hi = self._span_state(state, section)
+        self.bounds[lo:hi] = [(lb, ub)] * self.nodes[section]
+
+    def set_states_bounds_all_section(self, state, lb, ub):
+        for s in range(self.number_of_section):
+            self.set_states_bounds(state, s, lb, ub)
+
+    def set_controls_bounds(self, control, section, lb, ub):
+        u = self.unit_controls[section][control]
+        lb = lb / u if lb is not None else None
+        ub = ub / u if ub is not None else None
+        lo, hi = self._span_control(control, section)
+        self.bounds[lo:hi] = [(lb, ub)] * self.nodes[section]
+
+    def set_controls_bounds_all_section(self, control, lb, ub):
+        for s in range(self.number_of_section):
+            self.set_controls_bounds(control, s, lb, ub)
+
+    def set_time_final_bounds(self, section, lb, ub):
+        lb = lb / self.unit_time if lb is not None else 0.0
+        ub = ub / self.unit_time if ub is not None else None
+        self.bounds[self.index_time_final(section)] = (lb, ub)
+
+    def bounds_arrays(self):
+        """(lb, ub) float64 arrays with +-inf for None (scipy old_bound_to_new)."""
+        lb = np.array([-np.inf if b[0] is None else float(b[0]) for b in self.bounds])
+        ub = np.array([np.inf if b[1] is None else float(b[1]) for b in self.bounds])
+        return lb, ub
+
+    # ------------------------------------------------------------------ time helpers (:509-540)
+    def time_to_tau(self, time):
+        lo, hi = min(time), max(time)
+        mid = (lo + hi) / 2
+        return np.array([2 / (hi - lo) * (x - mid) for x in time])
+
+    def time_update(self):
+        self.time = []
+        t = [0] + self.time_final_all_section()
+        for i in range(self.number_of_section):
+            self.time.append((t[i + 1] - t[i]) / 2.0 * self.tau[i] + (t[i + 1] + t[i]) / 2.0)
+        return np.concatenate([i for i in self.time])
+
+    def time_knots(self):
+        return [0] + self.time_final_all_section()
+
+    # ------------------------------------------------------------------ index helpers (:542-572)
+    def index_states(self, state, section, index=None):
+        lo, hi = self._span_state(state, section)
+        if index is None:
+            return lo
+        assert index < hi - lo, "Error, index out of range"
+        if index < 0:
+            index = hi - lo + index
+        return lo + index
+
+    def index_controls(self, control, section, index=None):
+        lo, hi = self._span_control(control, section)
+        if index is None:
+            return lo
+        assert index < hi - lo, "Error, index out of range"
+        if index < 0:
+            index = hi - lo + index
+        return lo + index
+
+    def index_time_final(self, section):
+        return self.number_of_variables + range(-self.number_of_section, 0)[section]
+
+    # ------------------------------------------------------------------ unit scaling (:579-639)
+    def set_unit_states(self, state, section, value):
+        self.unit_states[section][state] = value
+
+    def set_unit_states_all_section(self, state, value):
+        for s in range(self.number_of_section):
+            self.set_unit_states(state, s, value)
+
+    def set_unit_controls(self, control, section, value):
+        self.unit_controls[section][control] = value
+
+    def set_unit_controls_all_section(self, control, value):
+        for s in range(self.number_of_section):
+            self.set_unit_controls(control, s, value)
+
+    def set_unit_time(self, value):
+        self.unit_time = value
+        ti = np.array(self.time_init) / value
+        self.time_init = list(ti)
+        self.time = []
+        for i in range(self.number_of_section):
+            self.time.append((ti[i + 1] - ti[i]) / 2.0 * self.tau[i] + (ti[i + 1] + ti[i]) / 2.0)
+        self.t0 = ti[0]
+        self.time_all_section = np.concatenate([t for t in self.time])
+        for s in range(self.number_of_section):
+            self.set_time_final(s, ti[s + 1] * value)
+
+    # ------------------------------------------------------------------ B200 engine
+    def _backend_name(self):
+        name = self.backend or os.environ.get("OGB200_BACKEND", "cuda")
+        if name not in ("cuda", "host"):
+            raise ValueError("backend must be 'cuda' or 'host', not %r" % (name,))
+        return name
+
+    def _check_callbacks(self):
+        assert len(self.dynamics) != 0, "It must be set dynamics"
+        assert self.cost is not None, "It must be set cost function"
+        assert self.equality is not None, "It must be set equality function"
+        assert self.inequality is not None, "It must be set inequality function"
+
+    def compile(self, obj, device=None):
+        """Trace the callbacks once and build the device engine (cuda backend only).
+        Returns an `engine.DeviceProblem`; raises if libogb200.so or a GPU is missing."""
+        from . import engine, tape
+        self._check_callbacks()
+        ir = tape.build_ir(self, obj)
+        self._engine = engine.DeviceProblem(ir, self.bounds_arrays(), device or self.device)
+        return self._engine
+
+    def evaluate_batch(self, P, obj=None, jacobian=True):
+        """Batched hot path: P (B, nvars) -> c (B, m+1) [, J (B, nvars, m+1)] as torch CUDA
+        tensors; row m carries cost / grad cost.  J[b, j, :] is column j."""
+        eng = self._engine if self._engine is not None else self.compile(obj)
+        return eng.eval_fd(P) if jacobian else eng.eval(P)
+
+    # ------------------------------------------------------------------ solve (:649-755)
+    def _dummy_func():
+        pass
+
+    def solve(self, obj, display_func=_dummy_func, **options):
+        """solve NLP with SciPy SLSQP; ftol (default 1e-6), maxiter (default 25)"""
+        self._check_callbacks()
+        if self._backend_name() == "cuda":
+            fun, cons, jac = self._device_callables(obj)
+        else:
+            fun, cons, jac = self._host_callables(obj)
+        ftol = options.setdefault("ftol", 1e-6)
+        maxiter = options.setdefault("maxiter", 25)
+        while self.iterator < self.maxIterator:
+            print("---- iteration : {0} ----".format(self.iterator + 1))
+            opt = optimize.minimize(fun, self.p, args=(self, obj), bounds=self.bounds,
+                                    constraints=cons, jac=jac, method="SLSQP",
+                                    options={"disp": True, "maxiter": maxiter, "ftol": ftol})
+            print(opt.message)
+            display_func()
+            print("")
+            if not (opt.status):
+                break
+            self.iterator += 1
+
+    def _device_callables(self, obj):
+        """SciPy-facing closures whose values AND Jacobians come from the CUDA kernels."""
+        eng = self.compile(obj)
+        meq, mineq, M = eng.meq, eng.mineq, eng.nrows
+        memo = {"cx": None, "c": None, "jx": None, "jc": None, "J": None}
+
+        def c_at(x):
+            self.p = x                                    # reference for_solver, :713
+            if memo["jx"] is not None and np.array_equal(memo["jx"], x):
+                return memo["jc"]
+            if memo["cx"] is None or not np.array_equal(memo["cx"], x):
+                memo["c"] = eng.eval_host(x)
+                memo["cx"] = np.array(x, copy=True)
+            return memo["c"]
+
+        def j_at(x):
+            self.p = x
+            if memo["jx"] is None or not np.array_equal(memo["jx"], x):
+                memo["jc"], memo["J"] = eng.eval_fd_host(x)
+                memo["jx"] = np.array(x, copy=True)
+            return memo["J"]
+
+        def fun(x, *a):
+            return float(c_at(x)[M - 1])
+
+        cons = ({"type": "eq", "fun": lambda x, *a: c_at(x)[:meq],
+                 "jac": lambda x, *a: j_at(x)[:, :meq].T, "args": (self, obj)},
+                {"type": "ineq", "fun": lambda x, *a: c_at(x)[meq:meq + mineq],
+                 "jac": lambda x, *a: j_at(x)[:, meq:meq + mineq].T, "args": (self, obj)})
+        if self.cost_derivative is None:
+            jac = lambda x, *a: j_at(x)[:, M - 1]
+        else:
+            def jac(x, *a):                               # user gradient, host (reference :733)
+                self.p = x
+                return self.cost_derivative(self, obj)
+        return fun, cons, jac
+
+    def _host_callables(self, obj):
+        """Explicit opt-in numpy path (BASELINE.json configs[0]): the reference's closures."""
+        def equality_add(p, *a):
+            self.p = p
+            rows = [np.atleast_1d(self.equality(self, obj))]
+            for s in range(self.number_of_section):
+                deriv = [self.D[s].dot(self.states(a_, s) / self.unit_states[s][a_])
+                         for a_ in range(self.number_of_states[s])]
+                tix = self.time_start(s) / self.unit_time
+                tfx = self.time_final(s) / self.unit_time
+                rows.append(np.concatenate(deriv) - (tfx - tix) / 2.0 * self.dynamics[s](self, obj, s))
+            for k in range(self.number_of_section - 1):
+                if self.number_of_states[k] != self.number_of_states[k + 1]:
+                    continue
+                for a_ in range(self.number_of_states[k]):
+                    prev = self.states(a_, k) / self.unit_states[k][a_]
+                    post = self.states(a_, k + 1) / self.unit_states[k][a_]
+                    if self.knot_states_smooth[k]:
+                        rows.append(np.atleast_1d(prev[-1] - post[0]))
+            return np.concatenate(rows)
+
+        def inequality(p, *a):
+            self.p = p
+            return self.inequality(self, obj)
+
+        def cost_add(p, *a):
+            self.p = p
+            base = self.cost(self, obj)
+            if self.running_cost is None:
+                return base
+            return base + sum(self.running_cost(self, obj) * np.concatenate([w for w in self.w]))
+
+        cons = ({"type": "eq", "fun": equality_add, "args": (self, obj)},
+                {"type": "ineq", "fun": inequality, "args": (self, obj)})
+        jac = None
+        if self.cost_derivative is not None:
+            def jac(p, *a):
+                self.p = p
+                return self.cost_derivative(self, obj)
+        return cost_add, cons, jac
+
+    # ------------------------------------------------------------------ reporting (:825-880)
+    def __repr__(self):
+        s = "---- parameter ----" + "\n"
+        s += "nodes = " + str(self.nodes) + "\n"
+        s += "number of states    = " + str(self.number_of_states) + "\n"
+        s += "number of controls  = " + str(self.number_of_controls) + "\n"
+        s += "number of sections  = " + str(self.number_of_section) + "\n"
+        s += "number of variables = " + str(self.number_of_variables) + "\n"
+        s += "---- algorithm ----" + "\n"
+        s += "max iteration = " + str(self.maxIterator) + "\n"
+        s += "---- function  ----" + "\n"
+        s += "dynamics        = " + str(self.dynamics) + "\n"
+        s += "cost            = " + str(self.cost) + "\n"
+        s += "cost_derivative = " + str(self.cost_derivative) + "\n"
+        s += "equality        = " + str(self.equality) + "\n"
+        s += "inequality      = " + str(self.inequality) + "\n"
+        s += "knot_states_smooth = " + str(self.dynamics) + "\n"
+        return s
+
+    def to_csv(self, filename="OpenGoddard_output.csv", delimiter=","):
+        cols = [self.time_update()]
+        header = "time, "
+        for i in range(self.number_of_states[0]):
+            header += "state%d, " % (i)
+            cols.append(self.states_all_section(i))
+        for i in range(self.number_of_controls[0]):
+            header += "control%d, " % (i)
+            cols.append(self.controls_all_section(i))
+        np.savetxt(filename, np.vstack(cols).T, delimiter=delimiter, header=header)
+        print("Completed saving \"%s\"" % (filename))
+
+    def plot(self, title_comment=""):
+        plt = _plt()
+        plt.figure()
+        plt.title("OpenGoddard inner variables" + title_comment)
+        plt.plot(self.p, "o")
+        plt.xlabel("variables")
+        plt.ylabel("value")
+        for section in range(self.number_of_section):
+            for line in self.div[section]:
+                plt.axvline(line, color="C%d" % ((section + 1) % 6), alpha=0.5)
+        plt.grid()
+
+
+class Guess:
+    """Initial-guess helpers (reference optimize.py:883-975)."""
+
+    @classmethod
+    def zeros(cls, time):
+        return np.zeros(len(time))
+
+    @classmethod
+    def constant(cls, time, const):
+        return np.ones(len(time)) * const
+
+    @classmethod
+    def linear(cls, time, y0, yf):
+        f = interpolate.interp1d(np.array([time[0], time[-1]]), np.array([y0, yf]))
+        return f(time)
+
+    @classmethod
+    def cubic(cls, time, y0, yprime0, yf, yprimef):
+        t0, tf = time[0], time[-1]
+        A = np.array([[1, t0, t0 ** 2, t0 ** 3], [0, 1, 2 * t0, 3 * t0 ** 2],
+                      [1, tf, tf ** 2, tf ** 3], [0, 1, 2 * tf, 3 * tf ** 2]])
+        C = np.linalg.inv(A).dot(np.array([y0, yprime0, yf, yprimef]))
+        return C[0] + C[1] * time + C[2] * time ** 2 + C[3] * time ** 3
+
+    @classmethod
+    def plot(cls, x, y, title="", xlabel="", ylabel=""):
+        plt = _plt()
+        plt.figure()
+        plt.plot(x, y, "-o")
+        plt.title(title)
+        plt.xlabel(xlabel)
+        plt.ylabel(ylabel)
+        plt.grid()
+
+
+class Condition(object):
+    """Row builder for user equality / inequality functions and dense cost gradients
+    (reference optimize.py:978-1072).  While the callbacks are being traced the rows are
+    symbolic and `__call__` returns them for the tape compiler."""
+
+    def __init__(self, length=0):
+        self._condition = np.zeros(length)
+        self._pieces = None
+
+    def add(self, arg, unit=1.0):
+        arg = arg / unit
+        if self._pieces is None and not _T.is_sym(arg):
+            self._condition = np.hstack((self._condition, arg))
+            return
+        if self._pieces is None:
+            self._pieces = [self._condition] if self._condition.size else []
+        self._pieces.append(arg)
+
+    def equal(self, arg1, arg2, unit=1.0):
+        self.add(arg1 - arg2, unit)
+
+    def lower_bound(self, arg1, arg2, unit=1.0):
+        self.add(arg1 - arg2, unit)
+
+    def upper_bound(self, arg1, arg2, unit=1.0):
+        self.add(arg2 - arg1, unit)
+
+    def change_value(self, index, value):
+        self._condition[index] = value
+
+    def __call__(self):
+        if self._pieces is not None:
+            return _T.SymRows(self._pieces)
+        return self._condition
+
+
+class Dynamics(object):
+    """Per-state right-hand-side holder (reference optimize.py:1075-1127)."""
+
+    def __init__(self, prob, section=0):
+        self.section = section
+        self.number_of_state = prob.number_of_states[section]
+        self.unit_states = prob.unit_states
+        self.unit_time = prob.unit_time
+        for i in range(self.number_of_state):
+            self.__dict__[i] = np.zeros(prob.nodes[section])
+
+    def __getitem__(self, key):
+        assert key < self.number_of_state, "Error, Dynamics key out of range"
+        return self.__dict__[key]
+
+    def __setitem__(self, key, value):
+        assert key < self.number_of_state, "Error, Dynamics key out of range"
+        self.__dict__[key] = value
+
+    def __call__(self):
+        rhs = [self.__dict__[i] * (self.unit_time / self.unit_states[self.section][i])
+               for i in range(self.number_of_state)]
+        if any(_T.is_sym(r) for r in rhs):
+            return _T.SymDynamics(self.section, rhs)
+        dx = np.zeros(0)
+        for r in rhs:
+            dx = np.hstack((dx, r))
+        return dx

@@ -1,0 +1,272 @@
+"""Lower traced expression DAGs (trace.py) to the register tapes of include/ogb200.h
+and assemble the problem IR the C ABI consumes.
+
+A tape is a straight-line program: one 64-bit word per instruction
+(op[63:56] dst[55:42] a[41:28] b[27:14] c[13:0]).  Registers are allocated by last
+use so a tape needs only as many registers as it has simultaneously live values.
+Operation order inside an expression is the user's (python evaluates left to right),
+so the device reproduces numpy's rounding.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import trace as T
+
+OPCODES = {
+    "nop": 0, "ldp": 1, "ldc": 2, "out": 3, "add": 4, "sub": 5, "mul": 6, "div": 7, "pow": 8,
+    "min": 9, "max": 10, "atan2": 11, "lt": 12, "le": 13, "gt": 14, "ge": 15, "eq": 16, "ne": 17,
+    "sel": 18, "neg": 19, "sqrt": 20, "exp": 21, "log": 22, "sin": 23, "cos": 24, "tan": 25,
+    "abs": 26, "square": 27, "recip": 28, "asin": 29, "acos": 30, "atan": 31, "sinh": 32,
+    "cosh": 33, "tanh": 34, "log10": 35, "sign": 36, "floor": 37, "ceil": 38, "and": 39,
+    "or": 40, "not": 41,
+}
+MAX_REG = 96
+MAX_FIELD = 16383
+
+OUT_DYN, OUT_EQ_POINT, OUT_INEQ_POINT, OUT_RUNNING, OUT_EQ_SCALAR, OUT_INEQ_SCALAR, OUT_COST = range(7)
+
+
+def _word(op, d=0, a=0, b=0, c=0):
+    for f in (d, a, b, c):
+        if f < 0 or f > MAX_FIELD:
+            raise ValueError("tape operand %d does not fit the 14-bit field" % f)
+    return (op << 56) | (d << 42) | (a << 28) | (b << 14) | c
+
+
+@dataclass
+class Tape:
+    code: np.ndarray            # uint64
+    consts: np.ndarray          # float64
+    outs: list                  # [(kind, row, glo, ghi)] ; slot i <-> outs[i]
+    nreg: int
+
+
+def compile_tape(out_nodes, outs, leaf_arg):
+    """out_nodes[i] feeds output slot i (described by outs[i]).
+    leaf_arg(node) -> LDP operand for a 'blk' / 'var' leaf."""
+    # ---- topological order (iterative post-order DFS), shared nodes once
+    order, seen = [], set()
+    for root in out_nodes:
+        stack = [(root, False)]
+        while stack:
+            n, done = stack.pop()
+            if done:
+                order.append(n)
+                continue
+            if n.uid in seen:
+                continue
+            seen.add(n.uid)
+            stack.append((n, True))
+            for a in reversed(n.args if n.op not in ("blk", "var", "const") else ()):
+                if a.uid not in seen:
+                    stack.append((a, False))
+    pos = {n.uid: i for i, n in enumerate(order)}
+    # ---- last use (outputs are emitted right after their node is available: see below)
+    last = {n.uid: pos[n.uid] for n in order}
+    for n in order:
+        if n.op not in ("blk", "var", "const"):
+            for a in n.args:
+                last[a.uid] = max(last[a.uid], pos[n.uid])
+    out_slots = {}
+    for slot, n in enumerate(out_nodes):
+        out_slots.setdefault(n.uid, []).append(slot)
+    # ---- emit
+    code, consts, cindex = [], [], {}
+    reg, free, nreg = {}, [], 0
+    for i, n in enumerate(order):
+        # operands whose last use is this instruction can donate their register
+        srcs = [reg[a.uid] for a in n.args] if n.op not in ("blk", "var", "const") else []
+        for a in (n.args if n.op not in ("blk", "var", "const") else ()):
+            if last[a.uid] == i and a.uid in reg:
+                r = reg.pop(a.uid)
+                free.append(r)
+        if free:
+            d = free.pop()
+        else:
+            d = nreg
+            nreg += 1
+        reg[n.uid] = d
+        if n.op == "const":
+            key = np.float64(n.value).tobytes()
+            if key not in cindex:
+                cindex[key] = len(consts)
+                consts.append(n.value)
+            code.append(_word(OPCODES["ldc"], d, cindex[key]))
+        elif n.op in ("blk", "var"):
+            code.append(_word(OPCODES["ldp"], d, leaf_arg(n)))
+        else:
+            s = srcs + [0] * (3 - len(srcs))
+            code.append(_word(OPCODES[n.op], d, s[0], s[1], s[2]))
+        for slot in out_slots.get(n.uid, ()):
+            code.append(_word(OPCODES["out"], slot, d))
+        if last[n.uid] == i:                # never read again (pure output / dead)
+            free.append(reg.pop(n.uid))
+    if nreg > MAX_REG:
+        raise T.TraceError("expression needs %d live registers (limit %d)" % (nreg, MAX_REG))
+    return Tape(np.array(code, dtype=np.uint64), np.array(consts, dtype=np.float64),
+                list(outs), max(nreg, 1))
+
+
+@dataclass
+class ProblemIR:
+    nodes: list
+    nstates: list
+    ncontrols: list
+    unit_states: list           # flattened over phases
+    unit_time: float
+    t0: float
+    knot_smooth: list
+    meq_user: int
+    mineq_user: int
+    has_running_cost: bool
+    node_tapes: list            # one Tape per phase
+    scalar_tape: Tape
+    nvars: int = 0
+    meta: dict = field(default_factory=dict)
+
+
+class _RowBuilder:
+    """Turns the ordered pieces of a traced Condition into output slots."""
+
+    def __init__(self, ctx, point_kind, scalar_kind):
+        self.ctx, self.point_kind, self.scalar_kind = ctx, point_kind, scalar_kind
+        self.nrows = 0
+        self.point = {s: [] for s in range(ctx.nsec)}   # per phase: (node, (kind,row,glo,ghi))
+        self.scalar = []                                # (node, (kind,row,0,0))
+
+    def _scalar(self, node):
+        self.scalar.append((node, (self.scalar_kind, self.nrows, 0, 0)))
+        self.nrows += 1
+
+    def add(self, piece):
+        g = self.ctx.graph
+        if isinstance(piece, T.Sym):
+            if piece.rng is None:
+                self._scalar(piece.parts)
+                return
+            local = all(all(l[0] == "blk" and l[1] == s for l in T.leaves(p))
+                        for s, p in piece.parts.items())
+            if local:
+                glo, ghi = piece.rng
+                if ghi > glo:
+                    for s, p in piece.parts.items():
+                        self.point[s].append((p, (self.point_kind, self.nrows, glo, ghi)))
+                    self.nrows += ghi - glo
+                return
+            piece = T.SymList.from_any(piece)
+        if isinstance(piece, T.SymList):
+            for e in piece.items:
+                self.add(e if isinstance(e, T.Sym) else float(e))
+            return
+        arr = np.atleast_1d(np.asarray(piece, dtype=float)).ravel()
+        for v in arr:
+            self._scalar(g.const(float(v)))
+
+
+def build_ir(prob, obj):
+    """Trace every callback of `prob` once and return the ProblemIR.
+    Row order = the reference's: user equality rows, defects per phase/state/node, knot
+    rows, user inequality rows, cost (optimize.py:670-698, :723-728)."""
+    from .optimize import Condition  # noqa: F401  (facade classes cooperate with the tracer)
+    ctx = T.TraceContext(prob)
+    view = T.TraceView(prob, ctx)
+    g = ctx.graph
+    nsec = ctx.nsec
+
+    # ---- dynamics: one call per phase (optimize.py:685)
+    dyn_nodes = []
+    for s in range(nsec):
+        fn = prob.dynamics[s]
+        if fn is None:
+            raise AssertionError("It must be set dynamics")
+        res = fn(view, obj, s)
+        rhs = []
+        if isinstance(res, T.SymDynamics):
+            items = res.rhs
+        else:
+            arr = np.asarray(res, dtype=float).reshape(ctx.nstates[s], ctx.nodes[s])
+            items = [row for row in arr]
+        if len(items) != ctx.nstates[s]:
+            raise T.TraceError("dynamics of phase %d returned %d states, expected %d"
+                               % (s, len(items), ctx.nstates[s]))
+        for a, it in enumerate(items):
+            if isinstance(it, T.Sym):
+                if it.rng is None:
+                    node = it.parts
+                elif it.rng == (ctx.g0[s], ctx.g0[s] + ctx.nodes[s]) and s in it.parts:
+                    node = it.parts[s]
+                else:
+                    raise T.TraceError("dynamics[%d] of phase %d is not a vector over that phase's nodes" % (a, s))
+                for lf in T.leaves(node):
+                    if lf[0] != "blk" or lf[1] != s:
+                        raise T.TraceError("dynamics of phase %d reads %r: only that phase's states/"
+                                           "controls at the same node are supported on the device" % (s, lf))
+            else:
+                arr = np.atleast_1d(np.asarray(it, dtype=float))
+                if not np.all(arr == arr.flat[0]):
+                    raise T.TraceError("dynamics[%d] is a non-uniform constant array (per-node data "
+                                       "tables are not supported on the device)" % a)
+                node = g.const(float(arr.flat[0]))
+            rhs.append(node)
+        dyn_nodes.append(rhs)
+
+    # ---- user rows
+    eq = _RowBuilder(ctx, OUT_EQ_POINT, OUT_EQ_SCALAR)
+    res = prob.equality(view, obj)
+    for piece in (res.pieces if isinstance(res, T.SymRows) else [res]):
+        eq.add(piece)
+    ineq = _RowBuilder(ctx, OUT_INEQ_POINT, OUT_INEQ_SCALAR)
+    res = prob.inequality(view, obj)
+    for piece in (res.pieces if isinstance(res, T.SymRows) else [res]):
+        ineq.add(piece)
+
+    # ---- cost (optimize.py:700-709)
+    cres = prob.cost(view, obj)
+    if isinstance(cres, T.Sym):
+        if cres.rng is not None:
+            raise T.TraceError("cost() must return a scalar")
+        cost_node = cres.parts
+    else:
+        cost_node = g.const(float(cres))
+    run_parts = None
+    if prob.running_cost is not None:
+        rres = prob.running_cost(view, obj)
+        if not (isinstance(rres, T.Sym) and rres.rng == (0, ctx.gtot)):
+            raise T.TraceError("running_cost() must return one value per node of every phase")
+        for s, p in rres.parts.items():
+            for lf in T.leaves(p):
+                if lf[0] != "blk" or lf[1] != s:
+                    raise T.TraceError("running_cost() must be pointwise in the node")
+        run_parts = rres.parts
+
+    # ---- tapes
+    node_tapes = []
+    for s in range(nsec):
+        nodes_out = list(dyn_nodes[s])
+        outs = [(OUT_DYN, a, 0, 0) for a in range(ctx.nstates[s])]
+        for rb in (eq, ineq):
+            for node, desc in rb.point[s]:
+                nodes_out.append(node)
+                outs.append(desc)
+        if run_parts is not None:
+            nodes_out.append(run_parts[s])
+            outs.append((OUT_RUNNING, 0, 0, 0))
+        node_tapes.append(compile_tape(nodes_out, outs, lambda n: n.args[1]))
+    sc_nodes = [n for n, _ in eq.scalar] + [n for n, _ in ineq.scalar] + [cost_node]
+    sc_outs = [d for _, d in eq.scalar] + [d for _, d in ineq.scalar] + [(OUT_COST, 0, 0, 0)]
+    for n in sc_nodes:
+        for lf in T.leaves(n):
+            if lf[0] != "var":
+                raise T.TraceError("internal: vector leaf in a scalar row")
+    scalar_tape = compile_tape(sc_nodes, sc_outs, lambda n: n.args[0])
+
+    units = [float(u) for s in range(nsec) for u in prob.unit_states[s][:ctx.nstates[s]]]
+    smooth = list(prob.knot_states_smooth) + [True] * nsec
+    return ProblemIR(
+        nodes=list(ctx.nodes), nstates=list(ctx.nstates), ncontrols=list(ctx.ncontrols),
+        unit_states=units, unit_time=float(prob.unit_time), t0=float(prob.t0),
+        knot_smooth=[bool(smooth[k]) for k in range(nsec - 1)],
+        meq_user=eq.nrows, mineq_user=ineq.nrows, has_running_cost=run_parts is not None,
+        node_tapes=node_tapes, scalar_tape=scalar_tape, nvars=ctx.nvars,
+        meta={"graph_nodes": len(g.nodes)})

@@ -1,0 +1,65 @@
+"""ctypes access to tests/emu/libogb_emu.so -- TEST INFRASTRUCTURE ONLY (see ogb_emu.cpp)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from opengoddard_b200 import capi
+
+EMU_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libogb_emu.so")
+_b = None
+
+
+def binding():
+    global _b
+    if _b is None:
+        from opengoddard_b200 import build
+        build.build_emu()
+        b = capi.Binding(EMU_LIB, "emu_")
+        dp = C.POINTER(C.c_double)
+        b.lib.emu_eval.restype = C.c_int
+        b.lib.emu_eval.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_int, dp, dp, C.c_int]
+        b.lib.emu_dx_gemm.restype = C.c_int
+        b.lib.emu_dx_gemm.argtypes = [C.c_void_p, dp, C.c_int, dp]
+        b.lib.emu_lgl_build.restype = C.c_int
+        b.lib.emu_lgl_build.argtypes = [C.c_int, dp, dp, dp]
+        _b = b
+    return _b
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class EmuProblem:
+    def __init__(self, ir, lb, ub):
+        self.b = binding()
+        self.h, self.info = self.b.create(ir)
+        self.lb = np.ascontiguousarray(lb, dtype=np.float64)
+        self.ub = np.ascontiguousarray(ub, dtype=np.float64)
+
+    def eval_fd(self, P, abs_step=1.4901161193847656e-08):
+        P = np.ascontiguousarray(np.atleast_2d(P), dtype=np.float64)
+        B, n, M = P.shape[0], self.info.nvars, self.info.nrows
+        assert P.shape[1] == n
+        c = np.empty((B, M))
+        J = np.empty((B, n, M))
+        rc = self.b.lib.emu_eval(self.h, _ptr(P), _ptr(self.lb), _ptr(self.ub), abs_step, B,
+                                 _ptr(c), _ptr(J), 1)
+        assert rc == 0
+        return c, J
+
+    def eval(self, P):
+        P = np.ascontiguousarray(np.atleast_2d(P), dtype=np.float64)
+        B, M = P.shape[0], self.info.nrows
+        c = np.empty((B, M))
+        rc = self.b.lib.emu_eval(self.h, _ptr(P), _ptr(self.lb), _ptr(self.ub), 0.0, B,
+                                 _ptr(c), _ptr(c), 0)
+        assert rc == 0
+        return c
+
+    def __del__(self):
+        try:
+            self.b.problem_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,114 @@
+"""Parity of the CUDA path (through the C ABI) against the committed golden vectors
+(generated from the unmodified reference + SciPy) and against the oracle on seeded
+batches.  Tolerances are the ones written in conftest.py."""
+import numpy as np
+import pytest
+
+from tests.helpers import (assert_c_close, assert_J_close, assert_lgl_close, golden, stacked_reference)
+
+pytestmark = pytest.mark.gpu
+
+CFGS = ["cfg1_brachistochrone20", "cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40",
+        "cfg5_lowthrust128", "ex05_goddard_knot25x2", "ex09_polar_tsto20x2", "ex10_lowthrust100"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+@pytest.mark.parametrize("N", [3, 4, 5, 8, 20, 25, 30, 40, 50, 64, 100, 128])
+def test_lgl_device_vs_reference(torch_cuda, N):
+    from opengoddard_b200 import engine
+    g = golden("lgl")
+    tau, w, D = engine.lgl_device(N)
+    assert_lgl_close(tau.cpu().numpy(), g["tau_%d" % N])
+    assert_lgl_close(w.cpu().numpy(), g["w_%d" % N])
+    assert_lgl_close(D.cpu().numpy(), g["D_%d" % N])
+    Dn = D.cpu().numpy()
+    inner = np.arange(1, N - 1)
+    assert (Dn[inner, inner] == 0.0).all()            # structural zeros exactly zero
+
+
+@pytest.mark.parametrize("name", CFGS)
+def test_eval_fd_vs_reference_golden(torch_cuda, api, name):
+    from opengoddard_b200 import workloads
+    g = golden("workload_" + name)
+    wl = workloads.build(name, api)
+    eng = wl.prob.compile(wl.obj)
+    c_ref, J_ref = stacked_reference(g)
+    c, J = eng.eval_fd(g["P"])
+    torch_cuda.cuda.synchronize()
+    assert_c_close(c.cpu().numpy(), c_ref, J_ref, g["P"])
+    assert_J_close(J.cpu().numpy().transpose(0, 2, 1), J_ref)
+    c_only = eng.eval(g["P"])
+    assert_c_close(c_only.cpu().numpy(), c_ref, J_ref, g["P"])
+
+
+@pytest.mark.parametrize("name", ["cfg2_goddard50", "cfg3_goddard_knot30x2"])
+def test_dx_gemm_tensor_core(torch_cuda, api, name):
+    """K1 (FP64 DMMA) against a plain fp64 matmul of the same operands."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build(name, api)
+    prob = wl.prob
+    eng = prob.compile(wl.obj)
+    P = workloads.make_batch(wl, 37)
+    DX = eng.dx_gemm(P).cpu().numpy()
+    ref = []
+    for s in range(prob.number_of_section):
+        for a in range(prob.number_of_states[s]):
+            lo = prob.index_states(a, s)
+            u = prob.unit_states[s][a]
+            ref.append(((P[:, lo:lo + prob.nodes[s]] * u) / u) @ prob.D[s].T)
+    ref = np.concatenate(ref, axis=1)
+    assert np.abs(DX - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name,B", [("cfg2_goddard50", 64), ("cfg3_goddard_knot30x2", 33),
+                                    ("cfg5_lowthrust128", 9), ("cfg4_polar3x40", 7)])
+def test_batch_vs_oracle(torch_cuda, api, name, B):
+    """Seeded jittered batch: CUDA path vs the numpy oracle on the same inputs (odd batch
+    sizes exercise the unaligned TMA head/tail handling)."""
+    from opengoddard_b200 import workloads
+    from oracle import og_numpy
+    wl = workloads.build(name, api)
+    wo = workloads.build(name, og_numpy)
+    P = workloads.make_batch(wl, B)
+    eng = wl.prob.compile(wl.obj)
+    c, J = eng.eval_fd(P)
+    c, J = c.cpu().numpy(), J.cpu().numpy()
+    lb, ub = og_numpy.bounds_arrays(wo.prob)
+    for b in sorted(set([0, 1, B // 2, B - 1])):
+        c_ref, J_ref = og_numpy.eval_fd(wo.prob, wo.obj, P[b], lb, ub)
+        assert_c_close(c[b], c_ref, J_ref, np.clip(P[b], lb, ub))
+        assert_J_close(J[b].T, J_ref)
+
+
+def test_full_size_properties(torch_cuda, api):
+    """BASELINE size (4096-instance Goddard-50): size-independent properties."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg2_goddard50", api)
+    eng = wl.prob.compile(wl.obj)
+    B = 4096
+    P = workloads.make_batch(wl, B)
+    c, J = eng.eval_fd(P)
+    c2, J2 = eng.eval_fd(P)
+    assert torch_cuda.equal(c, c2) and torch_cuda.equal(J, J2)          # deterministic
+    # batch invariance: a shard evaluated alone is bitwise identical to the same rows of the batch
+    lo, hi = 1000, 1517
+    cs, Js = eng.eval_fd(P[lo:hi])
+    assert torch_cuda.equal(cs, c[lo:hi]) and torch_cuda.equal(Js, J[lo:hi])
+    # every instance has the same structural sparsity as instance 0, all finite
+    assert torch_cuda.isfinite(J).all() and torch_cuda.isfinite(c).all()
+    nz0 = (J[0] != 0)
+    assert int(((J != 0) & ~nz0).sum()) == 0
+    # collocation rows are linear in the states: the state-column block of the defect rows is D
+    n0 = wl.prob.nodes[0]
+    meq_user = 5
+    blk = J[:, 0:n0, meq_user:meq_user + n0].cpu().numpy()      # d defect(h, i) / d h_k -> [b, k, i]
+    Dn = wl.prob.D[0]
+    off = ~np.eye(n0, dtype=bool)
+    err = np.abs(blk.transpose(0, 2, 1) - Dn[None])[:, off]
+    assert err.max() <= 1e-6 * np.abs(Dn).max()
