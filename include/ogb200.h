@@ -104,7 +104,7 @@ typedef struct ogb_problem_info {
     int32_t nrows;      /* meq + mineq + 1 (the last row carries cost / grad cost)    */
     int32_t ndx;        /* doubles of D.X per instance = sum_s nstates_s * nodes_s    */
     int32_t total_nodes;
-    int32_t tile_cols;  /* Jacobian columns staged per shared-memory tile             */
+    int32_t tile_cols;  /* warps per CTA of the sweep kernel (one column pipeline each) */
     int32_t group_cols; /* Jacobian columns per work item                             */
     int32_t smem_bytes; /* dynamic shared memory of the sweep kernel                  */
     int32_t ctas_per_sm;
@@ -126,6 +126,15 @@ int ogb_lgl_build_host(int N, double* tau_h, double* w_h, double* D_h);
 void* ogb_problem_create(const ogb_problem_desc* desc);
 void  ogb_problem_destroy(void* prob);
 int   ogb_problem_info_get(void* prob, ogb_problem_info* out);
+
+/* Tuning / verification knobs (not needed for normal use). */
+enum ogb_option {
+    OGB_OPT_GENERIC_COLUMNS = 0, /* 1: produce Jacobian columns with the generic per-row code instead of
+                                    the register-cached fast path (results must be bit-identical)     */
+    OGB_OPT_THREADS = 1,         /* CTA size of the sweep kernel: 64, 128, 192 or 256         */
+    OGB_OPT_GRID_CAP = 3         /* cap on the persistent grid (0 = SM count x resident CTAs)         */
+};
+int ogb_problem_set_option(void* prob, int key, int value);
 
 /* Scratch the caller must provide to ogb_eval / ogb_eval_fd for a batch of B.     */
 size_t ogb_workspace_bytes(void* prob, int B);

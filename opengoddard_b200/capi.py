@@ -135,6 +135,8 @@ def ogb():
         L.ogb_lgl_build_host.restype = C.c_int
         L.ogb_lgl_build_host.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
+        L.ogb_problem_set_option.restype = C.c_int
+        L.ogb_problem_set_option.argtypes = [vp, i32, i32]
         L.ogb_workspace_bytes.restype = C.c_size_t
         L.ogb_workspace_bytes.argtypes = [vp, i32]
         L.ogb_dx_gemm.restype = C.c_int

@@ -81,6 +81,9 @@ struct OgbWork {            // per work item scratch (shared memory on the devic
     double* scpert;         // [sc_nouts][npick] scalar-program outputs per perturbed pick
     double* pdlt;           // [G] change of the non-dimensional state operand of D.X (0 for controls / times)
     OgbCol* pcol;           // [G] production record of each column of the work item
+    double* cf;             // [ndx] (tf - t0)/2 * f at the base point, per defect row
+    double* rterm;          // [gtot] running-cost terms integrand * w at the base point
+    double* costp;          // [G] cost at the perturbed point of each column
     int G;
 };
 
@@ -311,11 +314,18 @@ OGB_HD void ogb_assemble_base(const OgbProb& P, const OgbWork& W, int tid, int n
         const double coef = W.coef[3 * s];
         for (int e = tid; e < S.ns * S.N; e += nthr) {
             const int a = e / S.N, i = e - a * S.N;
-            W.sc[S.rdef + e] = W.sdx[S.dxoff + e] - coef * W.sbase[a * P.gtot + S.g0 + i];
+            const double cf = coef * W.sbase[a * P.gtot + S.g0 + i];
+            W.cf[S.dxoff + e] = cf;
+            W.sc[S.rdef + e] = W.sdx[S.dxoff + e] - cf;
         }
         // user rows that are pointwise in the node
         for (int slot = S.ns; slot < S.nouts; ++slot) {
             const ogb_out o = P.outs[S.out_off + slot];
+            if (o.kind == OGB_OUT_RUNNING) {
+                for (int k = tid; k < S.N; k += nthr)
+                    W.rterm[S.g0 + k] = W.sbase[slot * P.gtot + S.g0 + k] * P.w[S.g0 + k];
+                continue;
+            }
             if (o.kind != OGB_OUT_EQ_POINT && o.kind != OGB_OUT_INEQ_POINT) continue;
             for (int k = tid; k < S.N; k += nthr) {
                 const int g = S.g0 + k;
@@ -333,113 +343,156 @@ OGB_HD void ogb_assemble_base(const OgbProb& P, const OgbWork& W, int tid, int n
         const ogb_out o = P.outs[P.sc_out_off + slot];
         if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR) W.sc[o.row] = W.scbase[slot];
     }
-    // cost = cost() + sum(running * w), summed left to right (optimize.py:700-709)
-    if (tid == 0) {
-        double cost = W.scbase[P.sc_cost_slot];
-        if (P.has_running) {
-            double acc = 0.0;
-            for (int g = 0; g < P.gtot; ++g) {
-                W.prefix[g] = acc;
-                const OgbSec& S = P.sec[ogb_sec_of_node(P, g)];
-                acc += W.sbase[S.run_slot * P.gtot + g] * P.w[g];
-            }
-            W.prefix[P.gtot] = acc;
-            cost = cost + acc;
+}
+
+// cost = cost() + sum(running * w), summed left to right like python's sum()
+// (optimize.py:700-709); one thread, after ogb_assemble_base.
+OGB_HD void ogb_assemble_cost(const OgbProb& P, const OgbWork& W) {
+    double cost = W.scbase[P.sc_cost_slot];
+    if (P.has_running) {
+        double acc = 0.0;
+        for (int g = 0; g < P.gtot; ++g) {
+            W.prefix[g] = acc;
+            acc += W.rterm[g];
         }
-        W.sc[P.M - 1] = cost;
+        W.prefix[P.gtot] = acc;
+        cost = cost + acc;
     }
+    W.sc[P.M - 1] = cost;
+}
+
+// cost at the perturbed point of column cl (one thread per column): the non-integrated
+// part from the perturbed scalar program if the variable is picked, the running sum redone
+// left to right with the one changed term so the rounding matches the reference's sum().
+OGB_HD bool ogb_col_moves_cost(const OgbProb& P, const OgbCol& cd) {
+    return cd.pick >= 0 || (P.has_running && cd.sec >= 0);
+}
+OGB_HD void ogb_cost_column(const OgbProb& P, const OgbWork& W, int cl) {
+    const OgbCol cd = W.pcol[cl];
+    if (!ogb_col_moves_cost(P, cd)) return;
+    double cost = cd.pick >= 0 ? W.scpert[P.sc_cost_slot * P.npick + cd.pick] : W.scbase[P.sc_cost_slot];
+    if (P.has_running) {
+        double acc = W.prefix[P.gtot];
+        if (cd.sec >= 0) {
+            const OgbSec& S = P.sec[cd.sec];
+            const int g = S.g0 + cd.k;
+            acc = W.prefix[g] + W.pert[S.run_slot * W.G + cl] * P.w[g];
+            for (int g2 = g + 1; g2 < P.gtot; ++g2) acc += W.rterm[g2];
+        }
+        cost = cost + acc;
+    }
+    W.costp[cl] = cost;
 }
 
 // ------------------------------------------------------------------ phase 4: one Jacobian column
 // Fills the non-zeros of column j into `col` (M doubles, pre-zeroed):
 //     col[r] = (c_r(x + h e_j) - c_r(x)) / dx          (_numdiff.py:708-711)
 // recomputing only the rows that can change.  `lane` / `nlanes` stride the work.
-OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl, double* col,
-                               int lane, int nlanes) {
-    const OgbCol cd = W.pcol[cl];
-    const double dx = W.pdx[cl];
-    const double x1 = W.px1[cl];
-    const int gt = P.gtot;
-    if (cd.sec >= 0) {
-        const OgbSec& S = P.sec[cd.sec];
-        const int k = cd.k, g = S.g0 + k, N = S.N;
-        const double coef = W.coef[3 * cd.sec];
-        const double dlt = W.pdlt[cl];
-        int a = -1;
-        if (cd.blk < S.ns) {                                   // a state: D.x moves in every node row
-            a = cd.blk;
-            const double* Dt = P.Dt + S.doff + k * N;          // column k of D
-            for (int i = lane; i < N; i += nlanes) {
-                if (i == k) continue;
-                const int e = a * N + i;
-                const double cp = (W.sdx[S.dxoff + e] + Dt[i] * dlt) - coef * W.sbase[a * gt + S.g0 + i];
-                col[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
-            }
-        }
-        for (int b = lane; b < S.ns; b += nlanes) {            // dynamics moved at node k only
-            const int e = b * N + k;
+
+// Where a column is being assembled: rows [0, meq) (user equalities, defects, knots) and
+// rows [meq, M) (user inequalities, cost) may live in different buffers (the CUDA kernel
+// stages them separately); tests/emu points both at one contiguous column.
+struct OgbColOut {
+    double* dense;          // rows [0, meq)
+    double* tail;           // rows [meq, M)
+    int meq;
+    OGB_HD void put(int r, double v) const {
+        if (r < meq) dense[r] = v; else tail[r - meq] = v;
+    }
+};
+
+// rows of state `a` at every node i != k: only D[i,k] * delta moves
+OGB_HD void ogb_scatter_drows(const OgbProb& P, const OgbWork& W, const OgbSec& S, int a, int k,
+                              double dlt, double dx, const OgbColOut& col, int lane, int nlanes) {
+    const double* Dt = P.Dt + S.doff + k * S.N;                // column k of D
+    for (int i = lane; i < S.N; i += nlanes) {
+        if (i == k) continue;
+        const int e = S.dxoff + a * S.N + i;
+        const double cp = (W.sdx[e] + Dt[i] * dlt) - W.cf[e];
+        col.dense[S.rdef + a * S.N + i] = (cp - W.sc[S.rdef + a * S.N + i]) / dx;
+    }
+}
+
+// rows living at node k: every state's defect row (dynamics moved) and the pointwise user rows
+OGB_HD void ogb_scatter_noderows(const OgbProb& P, const OgbWork& W, const OgbSec& S, int a, int k,
+                                 int cl, double dlt, double dx, const OgbColOut& col, int lane, int nlanes) {
+    const double coef = W.coef[3 * (int)(&S - P.sec)];
+    const int g = S.g0 + k;
+    for (int slot = lane; slot < S.nouts; slot += nlanes) {
+        if (slot < S.ns) {
+            const int e = slot * S.N + k;
             double dxp = W.sdx[S.dxoff + e];
-            if (b == a) dxp = dxp + P.D[S.doff + k * N + k] * dlt;
-            const double cp = dxp - coef * W.pert[b * W.G + cl];
-            col[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
-        }
-        for (int slot = S.ns + lane; slot < S.nouts; slot += nlanes) {
+            if (slot == a) dxp = dxp + P.D[S.doff + k * S.N + k] * dlt;
+            const double cp = dxp - coef * W.pert[slot * W.G + cl];
+            col.dense[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
+        } else {
             const ogb_out o = P.outs[S.out_off + slot];
             if ((o.kind == OGB_OUT_EQ_POINT || o.kind == OGB_OUT_INEQ_POINT) && g >= o.glo && g < o.ghi) {
                 const int r = o.row + (g - o.glo);
-                col[r] = (W.pert[slot * W.G + cl] - W.sc[r]) / dx;
-            }
-        }
-        for (int t = lane; t < P.nknot; t += nlanes) {
-            const OgbKnot K = P.knots[t];
-            if (K.var_prev == j || K.var_post == j) {
-                const double xp = K.var_prev == j ? x1 : W.sp[K.var_prev];
-                const double xq = K.var_post == j ? x1 : W.sp[K.var_post];
-                const double cp = ogb_nd(xp, K.u_prev) - (xq * K.u_post) / K.u_prev;
-                col[K.row] = (cp - W.sc[K.row]) / dx;
-            }
-        }
-    } else {                                                   // a final time: defects of <= 2 phases rescale
-        const double tfx1 = ogb_nd(x1, P.unit_time);
-        for (int s = cd.blk; s < P.nsec && s <= cd.blk + 1; ++s) {
-            const OgbSec& S = P.sec[s];
-            double coef1;
-            if (s == cd.blk) coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0;
-            else if (S.t0_idx == j) coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0;
-            else continue;
-            for (int e = lane; e < S.ns * S.N; e += nlanes) {
-                const int b = e / S.N, i = e - b * S.N;
-                const double cp = W.sdx[S.dxoff + e] - coef1 * W.sbase[b * gt + S.g0 + i];
-                col[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
+                col.put(r, (W.pert[slot * W.G + cl] - W.sc[r]) / dx);
             }
         }
     }
-    if (cd.pick >= 0) {                                        // rows of the scalar program
+}
+
+OGB_HD void ogb_scatter_knots(const OgbProb& P, const OgbWork& W, int j, double x1, double dx,
+                              const OgbColOut& col, int lane, int nlanes) {
+    for (int t = lane; t < P.nknot; t += nlanes) {
+        const OgbKnot K = P.knots[t];
+        if (K.var_prev == j || K.var_post == j) {
+            const double xp = K.var_prev == j ? x1 : W.sp[K.var_prev];
+            const double xq = K.var_post == j ? x1 : W.sp[K.var_post];
+            const double cp = ogb_nd(xp, K.u_prev) - (xq * K.u_post) / K.u_prev;
+            col.dense[K.row] = (cp - W.sc[K.row]) / dx;
+        }
+    }
+}
+
+// a final-time variable: the defects of its own phase and of the next one rescale
+OGB_HD void ogb_scatter_time(const OgbProb& P, const OgbWork& W, int j, int sec, double x1, double dx,
+                             const OgbColOut& col, int lane, int nlanes) {
+    const double tfx1 = ogb_nd(x1, P.unit_time);
+    for (int s = sec; s < P.nsec && s <= sec + 1; ++s) {
+        const OgbSec& S = P.sec[s];
+        double coef1;
+        if (s == sec) coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0;
+        else if (S.t0_idx == j) coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0;
+        else continue;
+        for (int e = lane; e < S.ns * S.N; e += nlanes) {
+            const int b = e / S.N, i = e - b * S.N;
+            const double cp = W.sdx[S.dxoff + e] - coef1 * W.sbase[b * P.gtot + S.g0 + i];
+            col.dense[S.rdef + e] = (cp - W.sc[S.rdef + e]) / dx;
+        }
+    }
+}
+
+// rows of the scalar program (picked variables only) and the cost row (the "+1" row)
+OGB_HD void ogb_scatter_scalar_cost(const OgbProb& P, const OgbWork& W, const OgbCol& cd, int cl,
+                                    double dx, const OgbColOut& col, int lane, int nlanes) {
+    if (cd.pick >= 0) {
         for (int slot = lane; slot < P.sc_nouts; slot += nlanes) {
             const ogb_out o = P.outs[P.sc_out_off + slot];
             if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR)
-                col[o.row] = (W.scpert[slot * P.npick + cd.pick] - W.sc[o.row]) / dx;
+                col.put(o.row, (W.scpert[slot * P.npick + cd.pick] - W.sc[o.row]) / dx);
         }
     }
-    if (lane == 0) {                                           // cost row (the "+1" row)
-        const bool run = P.has_running && cd.sec >= 0 && P.sec[cd.sec].run_slot >= 0;
-        if (cd.pick >= 0 || run) {
-            double cost = cd.pick >= 0 ? W.scpert[P.sc_cost_slot * P.npick + cd.pick]
-                                       : W.scbase[P.sc_cost_slot];
-            if (P.has_running) {
-                double acc = W.prefix[gt];
-                if (run) {
-                    const OgbSec& S = P.sec[cd.sec];
-                    const int g = S.g0 + cd.k;
-                    acc = W.prefix[g] + W.pert[S.run_slot * W.G + cl] * P.w[g];
-                    for (int g2 = g + 1; g2 < gt; ++g2) {
-                        const OgbSec& S2 = P.sec[ogb_sec_of_node(P, g2)];
-                        acc += W.sbase[S2.run_slot * gt + g2] * P.w[g2];
-                    }
-                }
-                cost = cost + acc;
-            }
-            col[P.M - 1] = (cost - W.sc[P.M - 1]) / dx;
-        }
+    if (lane == 0 && ogb_col_moves_cost(P, cd)) col.put(P.M - 1, (W.costp[cl] - W.sc[P.M - 1]) / dx);
+}
+
+OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl,
+                               const OgbColOut& col, int lane, int nlanes) {
+    const OgbCol cd = W.pcol[cl];
+    const double dx = W.pdx[cl];
+    const double x1 = W.px1[cl];
+    if (cd.sec >= 0) {
+        const OgbSec& S = P.sec[cd.sec];
+        const double dlt = W.pdlt[cl];
+        const int a = cd.blk < S.ns ? cd.blk : -1;
+        if (a >= 0) ogb_scatter_drows(P, W, S, a, cd.k, dlt, dx, col, lane, nlanes);
+        ogb_scatter_noderows(P, W, S, a, cd.k, cl, dlt, dx, col, lane, nlanes);
+        if (P.nknot) ogb_scatter_knots(P, W, j, x1, dx, col, lane, nlanes);
+    } else {
+        ogb_scatter_time(P, W, j, cd.blk, x1, dx, col, lane, nlanes);
     }
+    ogb_scatter_scalar_cost(P, W, cd, cl, dx, col, lane, nlanes);
 }

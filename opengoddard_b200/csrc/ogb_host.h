@@ -17,16 +17,17 @@
 #include "ogb_core.h"
 
 struct OgbPlan {
-    int threads;        // CTA size of the sweep kernel
+    int threads;        // CTA size of the sweep kernel (every warp produces Jacobian columns)
     int G;              // Jacobian columns per work item (perturbed-output staging capacity)
     int split;          // work items per instance = ceil(n / G)
-    int TC;             // columns per shared-memory tile
-    int nbuf;           // tile buffers in flight
+    int TC;             // warps per CTA
+    int nbuf;           // dense column buffers per warp
     size_t smem_bytes;  // dynamic shared memory
     int ctas_per_sm;
     // offsets (in doubles) into the dynamic shared memory block
     size_t o_cache, o_sp, o_sdx, o_sbase, o_sc, o_scbase, o_coef, o_prefix, o_pert, o_pdx, o_px1,
-        o_pdlt, o_pcol, o_scpert, o_tiles, tile_stride, o_end;
+        o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_slot, o_tiles, tile_stride, o_tail,
+        tail_stride, o_end;
 };
 
 struct OgbHostProblem {
@@ -51,65 +52,71 @@ struct OgbHostProblem {
 static inline size_t ogb_even(size_t x) { return (x + 1) & ~(size_t)1; }
 
 // Shared-memory plan of the sweep kernel for this problem size.
-//   descriptor cache | p | D.X | base outputs | c | scalar outs | coef | prefix |
-//   perturbed outputs [max_nouts][G] | dx, x1, dlt [G] | column records [G] |
-//   scalar perturbed outs | nbuf tiles of TC columns (+2 doubles alignment slack)
-static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts, size_t nouts,
-                                 OgbPlan* pl, std::string* err) {
-    const size_t SMEM_MAX = 227 * 1024;
-    pl->threads = 256;
+//   descriptor cache | 2 input stages (p, D.X) | base outputs | c | scalar outs | coef |
+//   prefix | perturbed outputs [max_nouts][G] | dx, x1, dlt, cost [G] | column records [G] |
+//   scalar perturbed outs | cf | rterm | slot table |
+static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, size_t nouts, int warps,
+                              OgbPlan* pl) {
+    size_t o = 0;
+    pl->o_cache = o;   o += ogb_even((size_t)P.nsec * sizeof(OgbSec) / 8) + ogb_even(nouts * 2) +
+                            ogb_even((size_t)P.nknot * sizeof(OgbKnot) / 8) + ogb_even(ncode) +
+                            ogb_even(nconsts);
+    pl->o_sp = o;      o += ogb_even(P.n + 2);
+    pl->o_sdx = o;     o += ogb_even(P.ndx + 2);
+    o += ogb_even(P.n + 2) + ogb_even(P.ndx + 2);          // second input stage
+    pl->o_sbase = o;   o += ogb_even((size_t)P.max_nouts * P.gtot);
+    pl->o_sc = o;      o += ogb_even(P.M);
+    pl->o_scbase = o;  o += ogb_even(P.sc_nouts + 1);
+    pl->o_coef = o;    o += ogb_even(3 * P.nsec);
+    pl->o_prefix = o;  o += ogb_even(P.gtot + 1);
+    pl->o_pert = o;    o += ogb_even((size_t)P.max_nouts * pl->G);
+    pl->o_pdx = o;     o += ogb_even(pl->G);
+    pl->o_px1 = o;     o += ogb_even(pl->G);
+    pl->o_pdlt = o;    o += ogb_even(pl->G);
+    pl->o_pcol = o;    o += (size_t)pl->G * 2;
+    pl->o_scpert = o;  o += ogb_even((size_t)P.sc_nouts * std::max(1, P.npick));
+    pl->o_cf = o;      o += ogb_even(P.ndx);
+    pl->o_rterm = o;   o += ogb_even(P.gtot);
+    pl->o_costp = o;   o += ogb_even(pl->G);
+    pl->o_slot = o;    o += nouts * 2;                     // int4 per output slot
+    pl->o_tiles = pl->o_tail = o;                          // (no column staging: J is written directly)
+    pl->tile_stride = pl->tail_stride = 0;
+    pl->o_end = o;
+    pl->smem_bytes = o * 8 + 16;   // + 2 mbarriers
+    pl->TC = warps;
+    pl->threads = warps * 32;
     pl->nbuf = 2;
+}
+
+static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts, size_t nouts,
+                                 OgbPlan* pl, std::string* err, int force_warps = 0) {
+    const size_t SMEM_MAX = 227 * 1024, SM_SMEM = 228 * 1024;
     const int GMAX = 224;
     pl->split = (P.n + GMAX - 1) / GMAX;
     pl->G = (P.n + pl->split - 1) / pl->split;
-    auto layout = [&](int tc) {
-        size_t o = 0;
-        pl->o_cache = o;   o += ogb_even((size_t)P.nsec * sizeof(OgbSec) / 8) + ogb_even(nouts * 2) +
-                                ogb_even((size_t)P.nknot * sizeof(OgbKnot) / 8) + ogb_even(ncode) +
-                                ogb_even(nconsts);
-        pl->o_sp = o;      o += ogb_even(P.n + 2);
-        pl->o_sdx = o;     o += ogb_even(P.ndx + 2);
-        pl->o_sbase = o;   o += ogb_even((size_t)P.max_nouts * P.gtot);
-        pl->o_sc = o;      o += ogb_even(P.M);
-        pl->o_scbase = o;  o += ogb_even(P.sc_nouts + 1);
-        pl->o_coef = o;    o += ogb_even(3 * P.nsec);
-        pl->o_prefix = o;  o += ogb_even(P.gtot + 1);
-        pl->o_pert = o;    o += ogb_even((size_t)P.max_nouts * pl->G);
-        pl->o_pdx = o;     o += ogb_even(pl->G);
-        pl->o_px1 = o;     o += ogb_even(pl->G);
-        pl->o_pdlt = o;    o += ogb_even(pl->G);
-        pl->o_pcol = o;    o += (size_t)pl->G * 2;
-        pl->o_scpert = o;  o += ogb_even((size_t)P.sc_nouts * std::max(1, P.npick));
-        pl->o_tiles = o;
-        pl->tile_stride = ogb_even((size_t)tc * P.M + 2);
-        o += pl->tile_stride * pl->nbuf;
-        pl->o_end = o;
-        pl->smem_bytes = o * 8 + 16;   // + mbarrier
-        pl->TC = tc;
-    };
-    // one column per warp per tile is the natural shape (8 warps); prefer the largest tile
-    // that still lets two CTAs share an SM, otherwise the largest that fits at all.
-    int best = 0;
-    for (int tc = 8; tc >= 1; --tc) {
-        layout(tc);
-        if (pl->smem_bytes + 1024 <= (228 * 1024) / 2) { best = tc; break; }
+    // pick the CTA size (2..8 warps) that keeps the most warps resident per SM; registers
+    // allow 768 threads per SM (<= 85 registers per thread)
+    int best_w = 0, best_res = 0;
+    for (int w = 8; w >= 2; w -= 2) {
+        if (force_warps && w != force_warps) continue;
+        ogb_layout(P, ncode, nconsts, nouts, w, pl);
+        if (pl->smem_bytes > SMEM_MAX) continue;
+        int ctas = (int)std::min<size_t>(16, SM_SMEM / (pl->smem_bytes + 1024));
+        ctas = std::min(ctas, 768 / (w * 32));
+        if (ctas < 1) continue;
+        const int res = ctas * w;
+        if (res > best_res) { best_res = res; best_w = w; }
     }
-    if (!best)
-        for (int tc = 8; tc >= 1; --tc) {
-            layout(tc);
-            if (pl->smem_bytes <= SMEM_MAX) { best = tc; break; }
-        }
-    if (!best) {
+    if (!best_w) {
+        ogb_layout(P, ncode, nconsts, nouts, 2, pl);
         char b[160];
         snprintf(b, sizeof b, "problem needs %zu B of shared memory per CTA (> %zu)", pl->smem_bytes,
                  SMEM_MAX);
         *err = b;
         return false;
     }
-    layout(best);
-    // 1 KB per CTA is reserved by the driver; 228 KB per SM
-    pl->ctas_per_sm = (int)std::min<size_t>(8, (228 * 1024) / (pl->smem_bytes + 1024));
-    if (pl->ctas_per_sm < 1) pl->ctas_per_sm = 1;
+    ogb_layout(P, ncode, nconsts, nouts, best_w, pl);
+    pl->ctas_per_sm = std::max(1, std::min((int)(SM_SMEM / (pl->smem_bytes + 1024)), 768 / pl->threads));
     return true;
 }
 

@@ -53,6 +53,10 @@ class DeviceProblem:
             pass
 
     # ------------------------------------------------------------------ helpers
+    def set_option(self, key, value):
+        """ogb_problem_set_option (include/ogb200.h): 0 generic columns, 1 threads, 3 grid cap."""
+        self._rc(self.b.lib.ogb_problem_set_option(self.h, int(key), int(value)), "ogb_problem_set_option")
+
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 

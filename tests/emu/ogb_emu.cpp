@@ -69,7 +69,9 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
     W.prefix = mem.data() + pl.o_prefix; W.pert = mem.data() + pl.o_pert; W.pdx = mem.data() + pl.o_pdx;
     W.px1 = mem.data() + pl.o_px1; W.scpert = mem.data() + pl.o_scpert; W.G = pl.G;
     W.pdlt = mem.data() + pl.o_pdlt; W.pcol = reinterpret_cast<OgbCol*>(mem.data() + pl.o_pcol);
-    double* tile = mem.data() + pl.o_tiles;
+    W.cf = mem.data() + pl.o_cf; W.rterm = mem.data() + pl.o_rterm; W.costp = mem.data() + pl.o_costp;
+    std::vector<double> tilev(P.M);
+    double* tile = tilev.data();
     std::vector<double> pclip(P.n), dxs(P.ndx);
     for (int b = 0; b < B; ++b) {
         for (int j = 0; j < P.n; ++j) {
@@ -86,10 +88,13 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
             for (int e = 0; e < P.ndx; ++e) W.sdx[e] = dxs[e];
             for (int q = 0; q < P.gtot + 1 + ncols; ++q) ogb_job(P, W, q, jlo, lb, ub, abs_step);
             ogb_assemble_base(P, W, 0, 1);
+            ogb_assemble_cost(P, W);
+            for (int cl = 0; cl < ncols; ++cl) ogb_cost_column(P, W, cl);
             if (ch == 0) memcpy(c + (size_t)b * P.M, W.sc, sizeof(double) * P.M);
             for (int cl = 0; cl < ncols; ++cl) {
                 for (int r = 0; r < P.M; ++r) tile[r] = 0.0;
-                ogb_scatter_column(P, W, jlo + cl, cl, tile, 0, 1);
+                OgbColOut out{tile, tile + P.meq, P.meq};
+                ogb_scatter_column(P, W, jlo + cl, cl, out, 0, 1);
                 memcpy(J + ((size_t)b * P.n + jlo + cl) * P.M, tile, sizeof(double) * P.M);
             }
         }

@@ -42,8 +42,13 @@ def assert_c_close(c, c_ref, J_ref=None, x=None):
         np.abs(c - c_ref) / np.maximum(scale, 1e-300)).max()
 
 
+J_DUST = 1e-7          # zero-pattern exceptions: a forward difference of two values that differ by an
+#                        ulp or not at all (|entry| <= J_DUST * rowmax) may be 0 on one side only, because
+#                        CUDA's and glibc's exp/sin/cos round differently in the last place
+
+
 def assert_J_close(J, J_ref):
-    """J, J_ref: (..., M, n).  Row-scaled tolerance + identical zero pattern."""
+    """J, J_ref: (..., M, n).  Row-scaled tolerance + identical zero pattern (up to FD dust)."""
     J, J_ref = np.asarray(J), np.asarray(J_ref)
     assert J.shape == J_ref.shape
     rowmax = np.abs(J_ref).max(axis=-1, keepdims=True)
@@ -51,8 +56,12 @@ def assert_J_close(J, J_ref):
     bad = err > J_RTOL * rowmax
     assert not bad.any(), "Jacobian mismatch: max row-scaled err %g" % (
         err / np.maximum(rowmax, 1e-300)).max()
-    assert ((J == 0) == (J_ref == 0)).all(), "Jacobian zero pattern differs in %d entries" % (
-        ((J == 0) != (J_ref == 0)).sum())
+    mism = (J == 0) != (J_ref == 0)
+    if mism.any():
+        big = np.maximum(np.abs(J), np.abs(J_ref)) > J_DUST * rowmax
+        assert not (mism & big).any(), "Jacobian zero pattern differs in %d entries (largest %g of rowmax)" % (
+            (mism & big).sum(), (np.maximum(np.abs(J), np.abs(J_ref)) / np.maximum(rowmax, 1e-300))[mism].max())
+        assert mism.sum() <= max(2, J.size // 100000), "too many dust-level zero-pattern differences: %d" % mism.sum()
 
 
 def assert_lgl_close(a, b):
