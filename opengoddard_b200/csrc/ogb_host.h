@@ -26,7 +26,7 @@ struct OgbPlan {
     int ctas_per_sm;
     // offsets (in doubles) into the dynamic shared memory block
     size_t o_cache, o_sp, o_sdx, o_sbase, o_sc, o_scbase, o_coef, o_prefix, o_pert, o_pdx, o_px1,
-        o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_slot, o_tiles, tile_stride, o_tail,
+        o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_prdx, o_slot, o_tiles, tile_stride, o_tail,
         tail_stride, o_end;
 };
 
@@ -78,6 +78,7 @@ static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, si
     pl->o_cf = o;      o += ogb_even(P.ndx);
     pl->o_rterm = o;   o += ogb_even(P.gtot);
     pl->o_costp = o;   o += ogb_even(pl->G);
+    pl->o_prdx = o;    o += ogb_even(pl->G);
     pl->o_slot = o;    o += nouts * 2;                     // int4 per output slot
     pl->o_tiles = pl->o_tail = o;                          // (no column staging: J is written directly)
     pl->tile_stride = pl->tail_stride = 0;

@@ -69,7 +69,7 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
     W.prefix = mem.data() + pl.o_prefix; W.pert = mem.data() + pl.o_pert; W.pdx = mem.data() + pl.o_pdx;
     W.px1 = mem.data() + pl.o_px1; W.scpert = mem.data() + pl.o_scpert; W.G = pl.G;
     W.pdlt = mem.data() + pl.o_pdlt; W.pcol = reinterpret_cast<OgbCol*>(mem.data() + pl.o_pcol);
-    W.cf = mem.data() + pl.o_cf; W.rterm = mem.data() + pl.o_rterm; W.costp = mem.data() + pl.o_costp;
+    W.cf = mem.data() + pl.o_cf; W.rterm = mem.data() + pl.o_rterm; W.costp = mem.data() + pl.o_costp; W.prdx = mem.data() + pl.o_prdx;
     std::vector<double> tilev(P.M);
     double* tile = tilev.data();
     std::vector<double> pclip(P.n), dxs(P.ndx);
