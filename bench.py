@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- collocation defect + FD-Jacobian evals/sec (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload NAME]
+    python bench.py --impl reference ...        # the CPU path (oracle port) on the host cores
+
+One *step* = one pass of the hot path over one batch of synthetic instances: for every
+instance the stacked vector c = [c_eq; c_ineq; cost] and its dense forward-difference
+Jacobian (K1 D.X GEMM + K2 fused sweep).  One *eval* = one instance of one step.
+
+Default workload: the 4096-instance Goddard 50-node batch (north_star's headline; the
+batch=1024 case of BASELINE.json configs[1] is `--batch 1024`).  Weak scaling: every
+rank evaluates its own B instances (shards of one seeded batch of N*B), no data-path
+collective; rank 0 prints ONE JSON line.
+
+Timing: W >= 3 warm-up steps, then exactly K timed steps, each bracketed by CUDA events
+on the launching stream; a 256 MiB memset flushes L2 between steps outside the event
+pairs (each step also writes ~3 GB, 24x L2).  Time = sum of the K event durations, MAX
+over ranks.  `e2e` repeats the measurement through the host-buffer API: pinned host p
+-> H2D -> kernels -> D2H of c and J into pinned host memory, all inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "collocation defect+FD-Jacobian evals/sec"
+UNIT = "evals/s"
+WORKLOADS = {                      # name -> (workloads.CONFIGS key, default batch)
+    "goddard50": ("cfg2_goddard50", 4096),
+    "goddard_knot30x2": ("cfg3_goddard_knot30x2", 4096),
+    "polar3x40": ("cfg4_polar3x40", 512),
+    "lowthrust128": ("cfg5_lowthrust128", 1024),
+    "brachistochrone20": ("cfg1_brachistochrone20", 4096),
+}
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def _cpu_worker(args):
+    """Evaluate a slice of the sample with the numpy oracle; returns (n_done, seconds)."""
+    cfg, first, count = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from opengoddard_b200 import workloads
+    from oracle import og_numpy
+    wl = workloads.build(cfg, og_numpy)
+    lb, ub = og_numpy.bounds_arrays(wl.prob)
+    P = workloads.make_batch(wl, count, first=first)
+    t0 = time.perf_counter()
+    for p in P:
+        og_numpy.eval_fd(wl.prob, wl.obj, p, lb, ub)
+    return count, time.perf_counter() - t0
+
+
+class CpuPool:
+    """Host worker processes (spawned once) that run the oracle port on seeded instances."""
+
+    def __init__(self, cfg, procs):
+        import multiprocessing as mp
+        self.cfg, self.procs = cfg, procs
+        self.pool = None
+        if procs > 1:
+            self.pool = mp.get_context("spawn").Pool(procs)
+            self.pool.map(_cpu_worker, [(cfg, 0, 1)] * procs)       # warm the workers (imports)
+        else:
+            _cpu_worker((cfg, 0, 1))
+
+    def run(self, sample, first=0):
+        """-> (evals/s over the wall clock, wall seconds, summed CPU seconds)"""
+        per = [sample // self.procs + (1 if r < sample % self.procs else 0) for r in range(self.procs)]
+        jobs = []
+        for k in per:
+            if k:
+                jobs.append((self.cfg, first, k))
+                first += k
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, jobs, chunksize=1) if self.pool else [_cpu_worker(j) for j in jobs]
+        wall = time.perf_counter() - t0
+        return sum(r[0] for r in res) / wall, wall, sum(r[1] for r in res)
+
+    def close(self):
+        if self.pool:
+            self.pool.close()
+            self.pool.join()
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    import numpy
+    import scipy
+    return {"cpu_model": model, "os_cpu_count": os.cpu_count(), "numpy": numpy.__version__,
+            "scipy": scipy.__version__, "omp_num_threads_per_worker": 1}
+
+
+def host_procs():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg, _ = WORKLOADS[args.workload]
+    procs = host_procs()
+    per_step = max(procs * 2, 32)                 # bounded sample per step
+    vals = []
+    pool = CpuPool(cfg, procs)
+    for _ in range(args.warmup):
+        pool.run(per_step)
+    for k in range(args.steps):
+        v, wall, _ = pool.run(per_step, first=k * per_step)
+        vals.append((v, wall))
+    pool.close()
+    total_wall = sum(w for _, w in vals)
+    value = per_step * len(vals) / total_wall
+    sample = "%d seeded instances of %s per step (oracle port, numpy + SciPy-restated FD), %d processes" % (
+        per_step, cfg, procs)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_wall / len(vals),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": "%s_b%d" % (args.workload, args.batch), "sample_per_step": per_step},
+           "cpu_baseline": dict(value=value, unit=UNIT, cores=procs, kind="port", sample=sample, **cpu_info()),
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------ the CUDA arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="goddard50", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: per workload)")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg, default_batch = WORKLOADS[args.workload]
+    if args.batch <= 0:
+        args.batch = default_batch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # CPU baseline first (rank 0 at N=1 only), before CUDA is touched in this process
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = host_procs()
+        sample = max(256, procs * 8)
+        pool = CpuPool(cfg, procs)
+        v_all, wall_all, cpu_s = pool.run(sample)
+        pool.close()
+        v_one, _, _ = CpuPool(cfg, 1).run(48)
+        cpu = dict(value=v_all, unit=UNIT, cores=procs, kind="port",
+                   sample="%d seeded instances of %s (same generator as the GPU batch), oracle port: numpy "
+                          "callbacks + restated SciPy 2-point FD for eq, ineq and cost; %.1f s of CPU work"
+                          % (sample, cfg, cpu_s),
+                   single_core_value=v_one, **cpu_info())
+
+    import numpy as np
+    import torch
+    import OpenGoddard.optimize as api
+    from opengoddard_b200 import workloads
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = workloads.build(cfg, api)
+    eng = wl.prob.compile(wl.obj, device=dev)
+    B = args.batch
+    # this rank's shard of the seeded global batch (instances rank*B .. rank*B + B - 1)
+    P_host = torch.from_numpy(workloads.make_batch(wl, B, first=rank * B)).pin_memory()
+    P = P_host.to(dev)
+    n, M = eng.nvars, eng.nrows
+    c = torch.empty((B, M), dtype=torch.float64, device=dev)
+    J = torch.empty((B, n, M), dtype=torch.float64, device=dev)
+    DX = torch.empty((B, eng.ndx), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    bytes_per_eval = 8 * n + 8 * M * (n + 1)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(timed):
+        """K1 then K2 on the current stream; returns (step event pair, sweep event pair)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
+        if timed:
+            ev[0].record()
+        eng.dx_gemm(P, out=DX, clip=True)
+        if timed:
+            ev[1].record()
+        eng.sweep_fd(P, DX, c, J)
+        if timed:
+            ev[2].record()
+        return ev
+
+    for _ in range(args.warmup):
+        step(False)
+        flush.zero_()
+    launches0 = eng.launches
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    events = []
+    for _ in range(args.steps):
+        events.append(step(True))
+        flush.zero_()                                   # L2 flush, outside the event pairs
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launches - launches0
+    step_ms = [e[0].elapsed_time(e[2]) for e in events]
+    sweep_ms = [e[1].elapsed_time(e[2]) for e in events]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer API (pinned host in, pinned host out)
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 8))
+    hc = torch.empty((B, M), dtype=torch.float64).pin_memory()
+    hJ = torch.empty((B, n, M), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        P.copy_(P_host, non_blocking=True)
+        eng.eval_fd(P, out_c=c, out_J=J)
+        hc.copy_(c, non_blocking=True)
+        hJ.copy_(J, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        sweep_avg_ms = sum(sweep_ms) / len(sweep_ms)
+        achieved = B * bytes_per_eval / (sweep_avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = "%s_b%d" % (args.workload, B)
+            traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s_b%d" % (args.workload, B), "instances_per_gpu": B, "nvars": n,
+                       "rows": M, "meq": eng.meq, "mineq": eng.mineq, "bytes_per_eval": bytes_per_eval,
+                       "l2": "256 MiB memset between timed steps (outside the event pairs); every step "
+                             "also writes %.2f GB of Jacobian (L2 is 126 MB)" % (B * bytes_per_eval / 1e9),
+                       "parallelism": "instance batch sharded over %d GPU(s), no data-path collective" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * n * 8,
+                    "d2h_bytes_per_step": B * M * 8 + B * n * M * 8, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "ogb_sweep_kernel (K2)",
+                         "kernel_ms": sweep_avg_ms, "bytes_per_launch": B * bytes_per_eval,
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

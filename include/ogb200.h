@@ -141,8 +141,16 @@ size_t ogb_workspace_bytes(void* prob, int B);
 
 /* K1: D.X for every phase and state of every instance as a batched FP64
  * tensor-core GEMM.  Replaces `D[i].dot(state_temp)` (reference optimize.py:680-682).
- * p [B, nvars] -> DX [B, ndx] (phase-major, then state-major, then node).         */
-int ogb_dx_gemm(void* prob, const double* p, int B, double* DX, void* stream);
+ * p [B, nvars] -> DX [B, ndx] (phase-major, then state-major, then node).  With lb / ub
+ * (both or neither) p is clipped into the bounds first, as ogb_eval_fd does.          */
+int ogb_dx_gemm(void* prob, const double* p, const double* lb, const double* ub, int B, double* DX,
+                void* stream);
+
+/* K2 alone (ogb_eval / ogb_eval_fd = ogb_dx_gemm + ogb_sweep on one stream), exposed so the
+ * dominant kernel can be timed and profiled by itself: DX must come from ogb_dx_gemm on the
+ * same p and bounds.  J == NULL: constraint vector only (no clipping).                 */
+int ogb_sweep(void* prob, const double* p, const double* DX, const double* lb, const double* ub,
+              double abs_step, int B, double* c, double* J, void* stream);
 
 /* c = [c_eq ; c_ineq ; cost] at every p[b] (no clipping).  Replaces the
  * `for_solver(equality_add)`, `for_solver(inequality)` and `for_solver(cost_add)`

@@ -140,7 +140,9 @@ def ogb():
         L.ogb_workspace_bytes.restype = C.c_size_t
         L.ogb_workspace_bytes.argtypes = [vp, i32]
         L.ogb_dx_gemm.restype = C.c_int
-        L.ogb_dx_gemm.argtypes = [vp, dp, i32, dp, vp]
+        L.ogb_dx_gemm.argtypes = [vp, dp, dp, dp, i32, dp, vp]
+        L.ogb_sweep.restype = C.c_int
+        L.ogb_sweep.argtypes = [vp, dp, dp, dp, dp, C.c_double, i32, dp, dp, vp]
         L.ogb_eval.restype = C.c_int
         L.ogb_eval.argtypes = [vp, dp, i32, dp, vp, vp]
         L.ogb_eval_fd.restype = C.c_int

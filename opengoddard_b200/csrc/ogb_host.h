@@ -191,6 +191,7 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
     P.meq = row;
     P.mineq = d->mineq_user;
     P.M = P.meq + P.mineq + 1;
+    if ((double)P.n * (double)P.M >= 4.0e9) { delete H; return fail("Jacobian of one instance exceeds 2^32 entries"); }
 
     // ---- tapes
     auto add_prog = [&](const ogb_program& pr, int* code_off, int* const_off, int* out_off) -> bool {

@@ -83,17 +83,30 @@ class DeviceProblem:
             raise capi.OgbError("%s failed: %s" % (what, self.b.error()))
 
     # ------------------------------------------------------------------ device API
-    def dx_gemm(self, P, out=None):
+    def dx_gemm(self, P, out=None, clip=False):
         """K1 alone: D.X for every phase/state of every instance -> (B, ndx)."""
         t = self.torch
         P = self._check_P(P)
         B = P.shape[0]
         DX = out if out is not None else t.empty((B, self.ndx), dtype=t.float64, device=self.device)
+        lb = self.lb.data_ptr() if clip else None
+        ub = self.ub.data_ptr() if clip else None
         with t.cuda.device(self.device):
-            self._rc(self.b.lib.ogb_dx_gemm(self.h, P.data_ptr(), B, DX.data_ptr(), self._stream()),
+            self._rc(self.b.lib.ogb_dx_gemm(self.h, P.data_ptr(), lb, ub, B, DX.data_ptr(), self._stream()),
                      "ogb_dx_gemm")
         self.launches += 1
         return DX
+
+    def sweep_fd(self, P, DX, out_c, out_J, abs_step=ABS_STEP):
+        """K2 alone on a D.X produced by dx_gemm(P, clip=True) (bench / profiling)."""
+        t = self.torch
+        P = self._check_P(P)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_sweep(self.h, P.data_ptr(), DX.data_ptr(), self.lb.data_ptr(),
+                                          self.ub.data_ptr(), float(abs_step), P.shape[0],
+                                          out_c.data_ptr(), out_J.data_ptr(), self._stream()), "ogb_sweep")
+        self.launches += 1
+        return out_c, out_J
 
     def eval(self, P, out=None):
         t = self.torch

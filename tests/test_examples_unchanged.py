@@ -1,0 +1,106 @@
+"""The reference's shipped example scripts, UNCHANGED, against the drop-in facade.
+
+Container-only (needs /root/reference/examples; skipped on the GPU box).  Every script
+is exec()'d with `from OpenGoddard.optimize import ...` resolving to the facade and
+`Problem.solve` intercepted at the point where the reference would call SciPy; the
+callbacks the script defined are then traced and lowered, and the device arithmetic (CPU
+emulation, tests/emu) must reproduce the c vector -- and for the BASELINE examples the
+FD Jacobian -- that the reference itself produced for that script (tests/golden/example_XX).
+Example 01 is additionally solved end to end on the explicit host backend."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+from tests.helpers import assert_c_close, assert_J_close, golden
+
+EXDIR = os.path.join(ref_loader.REFERENCE_ROOT, "examples")
+pytestmark = pytest.mark.skipif(not os.path.isdir(EXDIR), reason="reference examples only in the build container")
+
+
+def run_script(tag, intercept=True, env_backend=None):
+    import OpenGoddard.optimize as api
+    ref_loader.install_matplotlib_stub()
+    ref_loader.install_scipy_shims()
+    script = [f for f in sorted(os.listdir(EXDIR)) if f.startswith(tag) and f.endswith(".py")][0]
+    box = {}
+    real_solve = api.Problem.solve
+
+    def fake_solve(self, obj, display_func=None, **options):
+        box["prob"], box["obj"], box["options"] = self, obj, options
+
+    cwd = os.getcwd()
+    os.chdir(EXDIR)
+    if intercept:
+        api.Problem.solve = fake_solve
+    old = os.environ.get("OGB200_BACKEND")
+    if env_backend:
+        os.environ["OGB200_BACKEND"] = env_backend
+    out = io.StringIO()
+    try:
+        glb = {"__name__": "__main__", "__file__": script}
+        with contextlib.redirect_stdout(out):
+            try:
+                exec(compile(open(script).read(), script, "exec"), glb)
+            except Exception:
+                if intercept and "prob" in box:
+                    pass                      # post-processing on an unsolved problem may fail
+                else:
+                    raise
+    finally:
+        os.chdir(cwd)
+        api.Problem.solve = real_solve
+        if env_backend:
+            if old is None:
+                os.environ.pop("OGB200_BACKEND", None)
+            else:
+                os.environ["OGB200_BACKEND"] = old
+    return box, glb, out.getvalue()
+
+
+@pytest.mark.parametrize("tag", ["01", "02", "03", "04", "05", "06", "07", "08", "09", "10"])
+def test_example_traces_and_matches_reference(tag):
+    from opengoddard_b200 import tape
+    from tests.emu.emu import EmuProblem
+    e = golden("example_" + tag)
+    box, glb, _ = run_script(tag)
+    prob, obj = box["prob"], box["obj"]
+    assert np.allclose(prob.p, e["x0"], rtol=1e-12, atol=1e-15)   # guess built through the facade's LGL times
+    ir = tape.build_ir(prob, obj)
+    lb, ub = prob.bounds_arrays()
+    assert np.array_equal(lb, e["lb"]) and np.array_equal(ub, e["ub"])
+    emu = EmuProblem(ir, lb, ub)
+    assert emu.info.meq == e["c_eq"].size and emu.info.mineq == e["c_ineq"].size
+    x = np.clip(e["x0"], lb, ub)
+    c_ref = np.concatenate((e["c_eq"], e["c_ineq"], [e["cost"]]))
+    if "J_eq" in e.files:
+        J_ref = np.vstack((e["J_eq"], e["J_ineq"], e["g_cost"][None]))
+        c, J = emu.eval_fd(x)
+        assert_c_close(c[0], c_ref, J_ref, x)
+        assert_J_close(J[0].T, J_ref)
+    else:
+        c = emu.eval(x)
+        assert np.abs(c[0] - c_ref).max() <= 1e-9 * max(1.0, np.abs(c_ref).max())
+
+
+def test_example_01_runs_unchanged_end_to_end_on_host_backend():
+    box, glb, text = run_script("01", intercept=False, env_backend="host")
+    assert "Optimization terminated successfully" in text
+    prob = glb["prob"]
+    assert abs(prob.time_final(-1) - 1.7724608832526498) < 1e-5
+
+
+def test_example_11_table_lookup_is_reported_not_miscompiled():
+    """Example 11 interpolates data tables inside its dynamics (scipy interp1d): not traceable;
+    the facade must say so instead of producing wrong numbers."""
+    from opengoddard_b200 import tape, trace
+    try:
+        box, glb, _ = run_script("11")
+    except Exception as exc:                      # the script itself may not run in this container
+        pytest.skip("example 11 does not run here: %r" % (exc,))
+    with pytest.raises((trace.TraceError, TypeError, ValueError)):
+        tape.build_ir(box["prob"], box["obj"])

@@ -1,0 +1,193 @@
+"""Host-side mirror of the reference interface: layout, accessors, setters, units,
+bounds, quirks, Guess / Condition / Dynamics, tracing, and the explicit
+host backend (BASELINE.json configs[0]: brachistochrone, single instance, SciPy SLSQP)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from opengoddard_b200 import tape, trace, workloads
+from oracle import og_numpy
+from tests.helpers import golden
+
+
+def test_constructor_asserts(api):
+    with pytest.raises(AssertionError):
+        api.Problem((0.0, 1.0), [5], [1], [1])
+    with pytest.raises(AssertionError):
+        api.Problem([0.0, 1.0], [5, 5], [1], [1])
+    with pytest.raises(AssertionError):
+        api.Problem([0.0, 1.0], [5], [1, 1], [1])
+
+
+def test_layout_and_attributes_match_reference_semantics(api):
+    p = api.Problem([0.0, 1.0, 3.0], [4, 6], [2, 3], [1, 2], 7)
+    o = og_numpy.Problem([0.0, 1.0, 3.0], [4, 6], [2, 3], [1, 2], 7)
+    assert p.div == o.div == [[4, 8, 12], [18, 24, 30, 36, 42]]
+    assert p.number_of_variables == o.number_of_variables == 44
+    assert p.number_of_section == 2 and p.maxIterator == 7 and p.iterator == 0
+    assert p.bounds == o.bounds and p.bounds[-1] == (0.0, None) and p.bounds[0] == (None, None)
+    assert np.allclose(p.time_all_section, o.time_all_section, rtol=1e-13)
+    assert p.p[-2:].tolist() == [1.0, 3.0]
+    assert p.knot_states_smooth == [True] and p.dynamics == [None, None]
+    assert p.index_states(1, 1) == 18 and p.index_states(1, 1, -1) == 23
+    assert p.index_controls(1, 1, 2) == 38 and p.index_time_final(0) == 42 and p.index_time_final(-1) == 43
+    for name in ("nodes number_of_states number_of_controls tau w D time time_init t0 unit_states "
+                 "unit_controls unit_time cost running_cost cost_derivative equality inequality").split():
+        assert hasattr(p, name)
+
+
+def test_accessors_setters_units_and_quirks(api):
+    rng = np.random.default_rng(3)
+    p = api.Problem([0.0, 2.0, 5.0], [5, 7], [3, 3], [2, 2])
+    o = og_numpy.Problem([0.0, 2.0, 5.0], [5, 7], [3, 3], [2, 2])
+    for q in (p, o):
+        q.set_unit_states_all_section(0, 10.0)
+        q.set_unit_states(2, 1, 0.5)
+        q.set_unit_controls_all_section(1, 4.0)
+        q.set_unit_time(3.0)
+    vals = rng.standard_normal(12)
+    for q in (p, o):
+        q.set_states_all_section(1, vals)
+        q.set_states_all_section(0, np.concatenate((vals, vals)))     # longer than needed (quirk 10)
+        q.set_controls(1, 1, vals[:7])
+        q.set_time_final(0, 2.5)
+        q.set_states_bounds(2, 1, -1.0, None)
+        q.set_controls_bounds_all_section(1, None, 8.0)
+        q.set_time_final_bounds(1, None, 30.0)
+    assert np.array_equal(p.p, o.p) and p.bounds == o.bounds
+    for s in (0, 1, -1):
+        for a in (0, 1, 2, -1):                                       # states(-1, s): last block (quirk 3)
+            assert np.array_equal(p.states(a, s), o.states(a, s))
+        assert np.array_equal(p.controls(1, s), o.controls(1, s))
+        assert p.time_final(s) == o.time_final(s) and p.time_start(s) == o.time_start(s)
+    assert np.array_equal(p.states_all_section(-1), o.states_all_section(-1))
+    assert p.t0 == 0.0 and np.allclose(p.time_init, [0.0, 2 / 3, 5 / 3])
+    assert np.allclose(p.time_update(), np.concatenate([(t1 - t0) / 2 * tau + (t1 + t0) / 2 for t0, t1, tau in
+                                                        zip([0, 2.5], [2.5, 5.0], p.tau)]))
+    assert p.time_knots() == [0, 2.5, 5.0]
+    lb, ub = p.bounds_arrays()
+    assert lb[p.index_states(2, 1)] == -2.0 and np.isinf(ub[p.index_states(2, 1)])
+
+
+def test_guess_condition_dynamics_eager(api):
+    t = np.linspace(0.0, 2.0, 9)
+    assert np.array_equal(api.Guess.zeros(t), np.zeros(9))
+    assert np.array_equal(api.Guess.constant(t, 3.0), np.full(9, 3.0))
+    assert np.array_equal(api.Guess.linear(t, 1.0, 5.0), og_numpy.Guess.linear(t, 1.0, 5.0))
+    assert np.array_equal(api.Guess.cubic(t, 1.0, 0.5, 2.0, -1.0), og_numpy.Guess.cubic(t, 1.0, 0.5, 2.0, -1.0))
+    c = api.Condition()
+    c.equal(np.array([1.0, 2.0]), 0.5, unit=2.0)
+    c.lower_bound(3.0, 1.0)
+    c.upper_bound(np.array([1.0]), 4.0, unit=0.5)
+    assert np.allclose(c(), [0.25, 0.75, 2.0, 6.0])
+    g = api.Condition(4)
+    g.change_value(2, -1)
+    assert g().tolist() == [0, 0, -1, 0]
+    prob = api.Problem([0.0, 1.0], [4], [2], [1])
+    prob.set_unit_states(1, 0, 5.0)
+    prob.set_unit_time(2.0)
+    d = api.Dynamics(prob, 0)
+    d[0] = np.arange(4.0)
+    with pytest.raises(AssertionError):
+        d[2] = np.zeros(4)
+    assert np.allclose(d(), np.concatenate((np.arange(4.0) * 2.0, np.zeros(4))))
+
+
+def test_tracer_rejects_data_dependent_python(api):
+    wl = workloads.build("cfg1_brachistochrone20", api)
+
+    def bad_ineq(prob, obj):
+        y = prob.states_all_section(1)
+        if y[0] > 0:                      # python branch on a traced value
+            return y
+        return -y
+
+    wl.prob.inequality = bad_ineq
+    with pytest.raises(trace.TraceError):
+        tape.build_ir(wl.prob, wl.obj)
+
+
+def test_tracer_fallback_expands_non_local_rows(api):
+    """A row vector mixing node arrays with a picked scalar is not node-local: it is expanded
+    element by element into scalar rows and still matches the oracle (checked on the CPU
+    emulation of the device arithmetic)."""
+    from tests.emu.emu import EmuProblem
+
+    def build(mod):
+        wl = workloads.build("cfg1_brachistochrone20", mod)
+
+        def ineq(prob, obj):
+            x = prob.states_all_section(0)
+            y = prob.states_all_section(1)
+            r = mod.Condition()
+            r.lower_bound(y[1:], 0.0)              # sliced node range
+            r.upper_bound(x, x[-1] + 0.5)          # vector vs picked scalar -> expanded
+            r.lower_bound(np.sqrt(y ** 2 + 1.0) * x[3], -2.0)
+            r.lower_bound(prob.time_final(-1), 0.1)
+            return r()
+        wl.prob.inequality = ineq
+        return wl
+
+    wl, wo = build(api), build(og_numpy)
+    ir = tape.build_ir(wl.prob, wl.obj)
+    assert ir.mineq_user == 19 + 20 + 20 + 1
+    lb, ub = wl.prob.bounds_arrays()
+    P = workloads.make_batch(wl, 2, first=7)
+    c, J = EmuProblem(ir, lb, ub).eval_fd(P)
+    from tests.helpers import assert_c_close, assert_J_close
+    for b in range(2):
+        c_ref, J_ref = og_numpy.eval_fd(wo.prob, wo.obj, P[b], lb, ub)
+        assert_c_close(c[b], c_ref, J_ref, P[b])
+        assert_J_close(J[b].T, J_ref)
+
+
+def test_mask_assignment_and_where(api):
+    """`h[h < c] = c` (reference examples/09 air_density) and numpy.where trace to selects."""
+    prob = api.Problem([0.0, 1.0], [6], [1], [1])
+    ctx = trace.TraceContext(prob)
+    view = trace.TraceView(prob, ctx)
+    h = view.states(0, 0) - 3.0
+    h[h < -100.0] = -100.0
+    w = np.where(h > 0.0, h, 0.5 * h)
+    assert isinstance(w, trace.Sym) and w.rng == (0, 6)
+    assert ctx.graph.nodes[-1].op == "sel"
+
+
+def test_host_backend_brachistochrone_solves(api, monkeypatch):
+    """BASELINE.json configs[0]: single instance, host SciPy SLSQP, explicit host backend."""
+    monkeypatch.setenv("OGB200_BACKEND", "host")
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        wl.prob.solve(wl.obj)
+    text = out.getvalue()
+    assert "---- iteration : 1 ----" in text and "Optimization terminated successfully" in text
+    tf = wl.prob.time_final(-1)
+    assert abs(tf - np.sqrt(np.pi)) < 1e-4               # analytic optimum sqrt(pi); reference: 1.77246088
+    assert wl.prob.iterator >= 1
+
+
+def test_default_backend_needs_gpu(api, monkeypatch):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    monkeypatch.delenv("OGB200_BACKEND", raising=False)
+    from opengoddard_b200 import capi
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    with pytest.raises(capi.OgbError):
+        wl.prob.solve(wl.obj)
+
+
+def test_example_c_vectors_under_the_facade(api):
+    """The facade's eager accessors + Condition/Dynamics reproduce the shipped examples' c."""
+    for wname, ex in (("cfg2_goddard50", "04"), ("ex05_goddard_knot25x2", "05"), ("ex10_lowthrust100", "10")):
+        e = golden("example_" + ex)
+        wl = workloads.build(wname, api)
+        fun, cons, jac = wl.prob._host_callables(wl.obj)
+        x = np.clip(e["x0"], e["lb"], e["ub"])
+        # the facade's LGL basis is the library's (<= 1e-13 relative from the reference's)
+        assert np.allclose(cons[0]["fun"](x.copy()), e["c_eq"], rtol=0, atol=1e-8)
+        assert np.array_equal(cons[1]["fun"](x.copy()), e["c_ineq"])
+        assert abs(fun(x.copy()) - e["cost"]) <= 1e-12 * max(1.0, abs(float(e["cost"])))   # LGL weights differ by ulps
