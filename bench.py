@@ -116,49 +116,68 @@ def host_procs():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~2 ms; falls
+    back to one `nvidia-smi` query if the NVML binding is unavailable)."""
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+            "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.smax = index, [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for name, bit in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        if self.nv is None:
             try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                 r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                q = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
+                a, b = [float(x) for x in q.stdout.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1,
+                        "note": "single nvidia-smi query after the timed region (no NVML binding)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            try:
+                self._sample()
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------ reference arm
@@ -195,7 +214,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="goddard50", choices=sorted(WORKLOADS))

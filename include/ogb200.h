@@ -17,8 +17,10 @@
 #ifndef OGB200_H
 #define OGB200_H
 
+#ifndef __CUDACC_RTC__
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -108,6 +110,7 @@ typedef struct ogb_problem_info {
     int32_t group_cols; /* Jacobian columns per work item                             */
     int32_t smem_bytes; /* dynamic shared memory of the sweep kernel                  */
     int32_t ctas_per_sm;
+    int32_t jit;        /* 1: the tapes were compiled into the sweep kernel with NVRTC      */
 } ogb_problem_info;
 
 const char* ogb_last_error(void);
@@ -132,9 +135,16 @@ enum ogb_option {
     OGB_OPT_GENERIC_COLUMNS = 0, /* 1: produce Jacobian columns with the generic per-row code instead of
                                     the register-cached fast path (results must be bit-identical)     */
     OGB_OPT_THREADS = 1,         /* CTA size of the sweep kernel: 64, 128, 192 or 256         */
+    OGB_OPT_JIT = 2,             /* 1: run the NVRTC-specialised sweep kernel (tapes compiled to device
+                                    code), 0: the ahead-of-time kernel with the tape interpreter       */
     OGB_OPT_GRID_CAP = 3         /* cap on the persistent grid (0 = SM count x resident CTAs)         */
 };
 int ogb_problem_set_option(void* prob, int key, int value);
+
+/* Generate and NVRTC-compile the specialised sweep kernel for `desc` without loading it (works
+ * without a GPU).  Returns the cubin size (> 0) and copies the generated source into `log`, or a
+ * negative value and the compiler log.                                                      */
+int ogb_jit_check(const ogb_problem_desc* desc, char* log, int log_cap);
 
 /* Scratch the caller must provide to ogb_eval / ogb_eval_fd for a batch of B.     */
 size_t ogb_workspace_bytes(void* prob, int B);

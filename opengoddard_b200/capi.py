@@ -43,7 +43,7 @@ class OgbProblemDesc(C.Structure):
 
 class OgbProblemInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("nvars", "meq", "mineq", "nrows", "ndx", "total_nodes",
-                                          "tile_cols", "group_cols", "smem_bytes", "ctas_per_sm")]
+                                          "tile_cols", "group_cols", "smem_bytes", "ctas_per_sm", "jit")]
 
 
 class OgbError(RuntimeError):
@@ -137,6 +137,8 @@ def ogb():
                                          C.POINTER(C.c_double)]
         L.ogb_problem_set_option.restype = C.c_int
         L.ogb_problem_set_option.argtypes = [vp, i32, i32]
+        L.ogb_jit_check.restype = C.c_int
+        L.ogb_jit_check.argtypes = [C.POINTER(OgbProblemDesc), C.c_char_p, C.c_int]
         L.ogb_workspace_bytes.restype = C.c_size_t
         L.ogb_workspace_bytes.argtypes = [vp, i32]
         L.ogb_dx_gemm.restype = C.c_int
@@ -163,3 +165,15 @@ def lgl_host(N):
     if rc != 0:
         raise OgbError("ogb_lgl_build_host failed: " + b.error())
     return tau, w, D
+
+
+def jit_check(ir):
+    """NVRTC-compile the specialised sweep kernel for a traced problem (no GPU needed).
+    Returns (cubin_bytes, generated_source); raises OgbError with the compiler log."""
+    b = ogb()
+    desc, keep = make_desc(ir)
+    buf = C.create_string_buffer(1 << 20)
+    rc = b.lib.ogb_jit_check(C.byref(desc), buf, len(buf))
+    if rc <= 0:
+        raise OgbError("ogb_jit_check failed: " + b.error())
+    return rc, buf.value.decode()

@@ -11,8 +11,17 @@
 //   Dynamics.__call__ :1122-1127, Condition :1012-1066; SciPy FD stepping
 //   scipy/optimize/_numdiff.py:14-90,582-600,683-712.
 #pragma once
+#ifdef __CUDACC_RTC__                    // NVRTC: no host headers; math functions are built in
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned char uint8_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <math.h>
 #include <stdint.h>
+#endif
 
 #include "ogb200.h"
 
@@ -86,6 +95,21 @@ struct OgbWork {            // per work item scratch (shared memory on the devic
     double* costp;          // [G] cost at the perturbed point of each column
     double* prdx;           // [G] 1 / dx, correctly rounded (see ogb_fd_div)
     int G;
+};
+
+// launch plan of the sweep kernel (built by ogb_host.h, passed to the kernel by value)
+struct OgbPlan {
+    int threads;        // CTA size of the sweep kernel (every warp produces Jacobian columns)
+    int G;              // Jacobian columns per work item (perturbed-output staging capacity)
+    int split;          // work items per instance = ceil(n / G)
+    int TC;             // warps per CTA
+    int nbuf;           // dense column buffers per warp
+    unsigned long long smem_bytes;  // dynamic shared memory
+    int ctas_per_sm;
+    // offsets (in doubles) into the dynamic shared memory block
+    unsigned long long o_cache, o_sp, o_sdx, o_sbase, o_sc, o_scbase, o_coef, o_prefix, o_pert, o_pdx, o_px1,
+        o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_prdx, o_slot, o_tiles, tile_stride, o_tail,
+        tail_stride, o_end;
 };
 
 // ------------------------------------------------------------------ LGL basis
@@ -265,6 +289,23 @@ OGB_HD void ogb_dx_row(const OgbProb& P, const OgbSec& S, int a, const double* p
     }
 }
 
+// How the traced callbacks are executed: by the tape interpreter (ahead-of-time build), or --
+// when this header is compiled by NVRTC with OGB_JIT -- by straight-line device functions
+// generated from the same tapes (ogb_jit_node / ogb_jit_scalar are emitted by ogb_kernels.cu).
+#ifdef OGB_JIT
+template <class Load>
+__device__ __forceinline__ void ogb_jit_node(int sec, const Load& ld, double* out, int ostride);
+template <class Load>
+__device__ __forceinline__ void ogb_jit_scalar(const Load& ld, double* out, int ostride);
+#define OGB_NODE_PROGRAM(s, S, ld, out, stride) ogb_jit_node((s), (ld), (out), (stride))
+#define OGB_SCALAR_PROGRAM(ld, out, stride) ogb_jit_scalar((ld), (out), (stride))
+#else
+#define OGB_NODE_PROGRAM(s, S, ld, out, stride) \
+    ogb_run_tape(P.code + (S).code_off, (S).ncode, P.consts + (S).const_off, (ld), (out), (stride))
+#define OGB_SCALAR_PROGRAM(ld, out, stride) \
+    ogb_run_tape(P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, (ld), (out), (stride))
+#endif
+
 // ------------------------------------------------------------------ phase 2: tape jobs
 // Job q of a work item: q < gtot: node program at base node q; q == gtot: scalar program
 // at the base point + the per-phase time coefficients; q > gtot: Jacobian column
@@ -272,14 +313,13 @@ OGB_HD void ogb_dx_row(const OgbProb& P, const OgbSec& S, int a, const double* p
 OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
                     const double* lb, const double* ub, double abs_step) {
     if (q < P.gtot) {
-        const OgbSec& S = P.sec[ogb_sec_of_node(P, q)];
+        const int s = ogb_sec_of_node(P, q);
+        const OgbSec& S = P.sec[s];
         OgbNodeLoad ld{W.sp + S.off + (q - S.g0), S.N, -1, 0.0};
-        ogb_run_tape(P.code + S.code_off, S.ncode, P.consts + S.const_off, ld,
-                     W.sbase + q, P.gtot);
+        OGB_NODE_PROGRAM(s, S, ld, W.sbase + q, P.gtot);
     } else if (q == P.gtot) {
         OgbScalarLoad ld{W.sp, -1, 0.0};
-        ogb_run_tape(P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, ld,
-                     W.scbase, 1);
+        OGB_SCALAR_PROGRAM(ld, W.scbase, 1);
         for (int s = 0; s < P.nsec; ++s) {
             const OgbSec& S = P.sec[s];
             const double tfx = ogb_nd(W.sp[S.tf_idx], P.unit_time);                 // :684
@@ -307,14 +347,12 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
                 dlt = ogb_nd(x1, u) - ogb_nd(x0, u);
             }
             OgbNodeLoad ld{W.sp + S.off + col.k, S.N, col.blk, x1};
-            ogb_run_tape(P.code + S.code_off, S.ncode, P.consts + S.const_off, ld,
-                         W.pert + cl, W.G);
+            OGB_NODE_PROGRAM(col.sec, S, ld, W.pert + cl, W.G);
         }
         W.pdlt[cl] = dlt;
         if (col.pick >= 0) {
             OgbScalarLoad ld{W.sp, j, x1};
-            ogb_run_tape(P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, ld,
-                         W.scpert + col.pick, P.npick);
+            OGB_SCALAR_PROGRAM(ld, W.scpert + col.pick, P.npick);
         }
     }
 }

@@ -16,20 +16,6 @@
 
 #include "ogb_core.h"
 
-struct OgbPlan {
-    int threads;        // CTA size of the sweep kernel (every warp produces Jacobian columns)
-    int G;              // Jacobian columns per work item (perturbed-output staging capacity)
-    int split;          // work items per instance = ceil(n / G)
-    int TC;             // warps per CTA
-    int nbuf;           // dense column buffers per warp
-    size_t smem_bytes;  // dynamic shared memory
-    int ctas_per_sm;
-    // offsets (in doubles) into the dynamic shared memory block
-    size_t o_cache, o_sp, o_sdx, o_sbase, o_sc, o_scbase, o_coef, o_prefix, o_pert, o_pdx, o_px1,
-        o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_prdx, o_slot, o_tiles, tile_stride, o_tail,
-        tail_stride, o_end;
-};
-
 struct OgbHostProblem {
     std::vector<OgbSec> sec;
     std::vector<ogb_out> outs;

@@ -29,7 +29,7 @@ int emu_problem_info_get(void* h, ogb_problem_info* o) {
     o->nvars = H->P.n; o->meq = H->P.meq; o->mineq = H->P.mineq; o->nrows = H->P.M;
     o->ndx = H->P.ndx; o->total_nodes = H->P.gtot; o->tile_cols = H->plan.TC;
     o->group_cols = H->plan.G; o->smem_bytes = (int)H->plan.smem_bytes;
-    o->ctas_per_sm = H->plan.ctas_per_sm;
+    o->ctas_per_sm = H->plan.ctas_per_sm; o->jit = 0;
     return 0;
 }
 

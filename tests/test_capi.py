@@ -24,7 +24,7 @@ def test_header_declares_the_documented_entry_points():
     names = declared_functions()
     for n in ("ogb_last_error", "ogb_version", "ogb_lgl_build", "ogb_lgl_build_host", "ogb_problem_create",
               "ogb_problem_destroy", "ogb_problem_info_get", "ogb_problem_set_option", "ogb_workspace_bytes",
-              "ogb_dx_gemm", "ogb_sweep", "ogb_eval", "ogb_eval_fd"):
+              "ogb_dx_gemm", "ogb_sweep", "ogb_eval", "ogb_eval_fd", "ogb_jit_check"):
         assert n in names
 
 
@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     # sizes the C side static_asserts on are mirrored here: 4 x int32, pointer + int32 pairs
     assert ctypes.sizeof(capi.OgbOut) == 16
-    assert ctypes.sizeof(capi.OgbProblemInfo) == 40
+    assert ctypes.sizeof(capi.OgbProblemInfo) == 44
     assert ctypes.sizeof(capi.OgbProgram) == 6 * 8 + 8 if False else ctypes.sizeof(capi.OgbProgram) % 8 == 0
 
 
@@ -71,3 +71,19 @@ def test_no_gpu_means_error_not_fallback(api):
         wl.prob.compile(wl.obj)
     with pytest.raises(capi.OgbError):
         wl.prob.evaluate_batch(np.zeros((2, wl.prob.number_of_variables)), wl.obj)
+
+
+@pytest.mark.parametrize("name", ["cfg2_goddard50", "ex09_polar_tsto20x2"])
+def test_jit_source_compiles_for_sm100a_without_a_gpu(api, name):
+    """The traced tapes lower to CUDA source that NVRTC compiles for sm_100a (no GPU needed)."""
+    from opengoddard_b200 import tape, workloads
+    wl = workloads.build(name, api)
+    ir = tape.build_ir(wl.prob, wl.obj)
+    try:
+        nbytes, src = capi.jit_check(ir)
+    except capi.OgbError as e:
+        if "libnvrtc not found" in str(e):
+            pytest.skip("NVRTC is not installed here")
+        raise
+    assert nbytes > 10000
+    assert "ogb_jit_node_0" in src and "ogb_jit_scalar" in src and "exp(" in src

@@ -47,6 +47,21 @@ def test_eval_fd_vs_reference_golden(torch_cuda, api, name):
     assert_c_close(c_only.cpu().numpy(), c_ref, J_ref, g["P"])
 
 
+@pytest.mark.parametrize("name", ["cfg3_goddard_knot30x2", "cfg4_polar3x40", "cfg5_lowthrust128"])
+def test_jit_and_interpreter_kernels_agree(torch_cuda, api, name):
+    from opengoddard_b200 import workloads
+    wl = workloads.build(name, api)
+    eng = wl.prob.compile(wl.obj)
+    assert eng.info.jit == 1
+    P = workloads.make_batch(wl, 21)
+    c1, J1 = eng.eval_fd(P)
+    e1 = eng.eval(P)
+    eng.set_option(2, 0)
+    c0, J0 = eng.eval_fd(P)
+    e0 = eng.eval(P)
+    assert torch_cuda.equal(c0, c1) and torch_cuda.equal(J0, J1) and torch_cuda.equal(e0, e1)
+
+
 @pytest.mark.parametrize("name", ["cfg2_goddard50", "cfg3_goddard_knot30x2"])
 def test_dx_gemm_tensor_core(torch_cuda, api, name):
     """K1 (FP64 DMMA) against a plain fp64 matmul of the same operands."""
@@ -114,6 +129,12 @@ def test_full_size_properties(torch_cuda, api):
     cg, Jg = eng.eval_fd(P[:300])
     eng.set_option(0, 0)
     assert torch_cuda.equal(cg, c[:300]) and torch_cuda.equal(Jg, J[:300])
+    # the NVRTC-compiled tapes and the tape interpreter agree bit for bit
+    assert eng.info.jit == 1, "NVRTC specialisation did not engage on the GPU box"
+    eng.set_option(2, 0)
+    ci, Ji = eng.eval_fd(P[:300])
+    eng.set_option(2, 1)
+    assert torch_cuda.equal(ci, c[:300]) and torch_cuda.equal(Ji, J[:300])
     # collocation rows are linear in the states: the state-column block of the defect rows is D
     n0 = wl.prob.nodes[0]
     meq_user = 5
@@ -132,7 +153,8 @@ def test_solve_uses_device_jacobians(torch_cuda, api, capsys):
     wl.prob.solve(wl.obj)
     text = capsys.readouterr().out
     assert "Optimization terminated successfully" in text
-    assert abs(wl.prob.time_final(-1) - 1.7724608832526498) < 1e-5
+    # SLSQP stops at ftol = 1e-6 on the cost (= t_f); the reference run ends at 1.77246088, analytic 1.77245385
+    assert abs(wl.prob.time_final(-1) - 1.7724608832526498) < 1e-4
     assert wl.prob._engine.launches > 10
 
 
