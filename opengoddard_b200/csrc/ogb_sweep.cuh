@@ -73,6 +73,13 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                  int B, double* __restrict__ c, double* __restrict__ J, int with_fd,
                  int ncode, int nconsts, int nouts, int force_generic) {
     extern __shared__ __align__(16) double smem[];
+#ifdef OGB_SPEC_M                     // NVRTC build: the problem's sizes are compile-time constants
+    P.M = OGB_SPEC_M; P.n = OGB_SPEC_NVARS; P.meq = OGB_SPEC_MEQ; P.mineq = OGB_SPEC_MINEQ;
+    P.gtot = OGB_SPEC_GTOT; P.ndx = OGB_SPEC_NDX; P.nsec = OGB_SPEC_NSEC; P.nknot = OGB_SPEC_NKNOT;
+    P.npick = OGB_SPEC_NPICK; P.has_running = OGB_SPEC_RUNNING; P.sc_nouts = OGB_SPEC_SC_NOUTS;
+    P.sc_cost_slot = OGB_SPEC_SC_COST_SLOT; P.max_nouts = OGB_SPEC_MAX_NOUTS;
+    pl.G = OGB_SPEC_G; pl.split = OGB_SPEC_SPLIT;
+#endif
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     OgbWork W;
@@ -142,6 +149,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     const int meq = P.meq;
 
     if ((long)blockIdx.x < nitems) stage_inputs(blockIdx.x, 0);
+    __syncthreads();                 // the odd head / tail doubles of the first item are in place
     unsigned it = 0;
     for (long item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const long b = item / nchunk;
@@ -159,32 +167,35 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             W.sp = smem + pl.o_sp + st * in_stride + (int)((reinterpret_cast<uintptr_t>(gp) >> 3) & 1);
             W.sdx = smem + pl.o_sdx + st * in_stride + (int)((reinterpret_cast<uintptr_t>(gdx) >> 3) & 1);
         }
-        mbar_wait(mbar + st, (it >> 1) & 1u);
-        __syncthreads();
+        mbar_wait(mbar + st, (it >> 1) & 1u);      // TMA bytes are visible to every thread that waited
         if (with_fd) {               // _check_clip_x (scipy/optimize/_slsqp_py.py:355)
             for (int j = tid; j < n; j += nthr) {
                 const double x = W.sp[j], lo = lb[j], hi = ub[j];
                 W.sp[j] = x < lo ? lo : (x > hi ? hi : x);
             }
-            __syncthreads();
         }
+        __syncthreads();
 
         // ---- phase 2: tapes -- base nodes, scalar program, one job per Jacobian column
         for (int q = tid; q < P.gtot + 1 + ncols; q += nthr) ogb_job(P, W, q, jlo, lb, ub, abs_step);
         __syncthreads();
 
-        // ---- phase 3: c at the base point, then the perturbed cost of every column
+        // ---- phase 3: c at the base point and the perturbed cost of every column.  Without a
+        //      running cost neither depends on the other, so one barrier covers both.
         ogb_assemble_base(P, W, tid, nthr);
+        if (!P.has_running) {
+            if (tid == 0) ogb_assemble_cost(P, W);
+            for (int cl = tid; cl < ncols; cl += nthr) ogb_cost_column(P, W, cl);
+        }
         __syncthreads();
-        if (tid == 0) ogb_assemble_cost(P, W);
-        if (ch == 0)
-            for (int r = tid; r < M - 1; r += nthr) c[b * M + r] = W.sc[r];
-        __syncthreads();
-        if (ch == 0 && tid == 0) c[b * M + M - 1] = W.sc[M - 1];
-        if (ncols > 0) {
+        if (P.has_running) {
+            if (tid == 0) ogb_assemble_cost(P, W);
+            __syncthreads();
             for (int cl = tid; cl < ncols; cl += nthr) ogb_cost_column(P, W, cl);
             __syncthreads();
         }
+        if (ch == 0)
+            for (int r = tid; r < M; r += nthr) c[b * M + r] = W.sc[r];
 
         // ---- phase 4: Jacobian columns, one warp per column (columns warp, warp + nwarps, ...),
         //      no block barrier and no staging: the warp streams the column's zeros to HBM with

@@ -4,6 +4,10 @@ PyTorch is plumbing here (device memory, streams, pinned staging buffers); all
 arithmetic happens in the sm_100a kernels behind the C ABI (include/ogb200.h).
 Everything raises if CUDA or the library is unavailable -- there is no CPU fallback.
 """
+import ctypes as C
+import os
+import warnings
+
 import numpy as np
 
 from . import capi
@@ -19,7 +23,10 @@ class DeviceProblem:
     J[b, j, :] is the column of variable j; rows are [c_eq ; c_ineq ; cost].
     """
 
-    def __init__(self, ir, bounds, device=None):
+    def __init__(self, ir, bounds, device=None, jit=True):
+        """jit: compile the traced tapes into the sweep kernel with NVRTC (about 1-2 s once per
+        distinct problem; worth it for batches, not for one single-instance solve).
+        $OGB200_JIT = 0 forces the interpreter kernel, = require makes a JIT failure an error."""
         import torch
         self.torch = torch
         self.b = capi.ogb()                       # raises OgbError if the .so is missing
@@ -43,6 +50,18 @@ class DeviceProblem:
         self._work = None
         self._one = None
         self.launches = 0                         # kernels launched through this handle
+        mode = os.environ.get("OGB200_JIT", "")
+        self.jit_error = None
+        if mode != "0" and (jit or mode == "require"):
+            try:
+                self.set_option(2, 1)
+                self.b.problem_info_get(self.h, C.byref(self.info))
+            except capi.OgbError as e:
+                if mode == "require":
+                    raise
+                self.jit_error = str(e)
+                warnings.warn("OpenGoddard-B200: NVRTC specialisation unavailable (%s); using the "
+                              "tape-interpreter kernel" % e, RuntimeWarning)
 
     def __del__(self):
         try:

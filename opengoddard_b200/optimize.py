@@ -310,13 +310,14 @@ class Problem:
         assert self.equality is not None, "It must be set equality function"
         assert self.inequality is not None, "It must be set inequality function"
 
-    def compile(self, obj, device=None):
+    def compile(self, obj, device=None, jit=True):
         """Trace the callbacks once and build the device engine (cuda backend only).
-        Returns an `engine.DeviceProblem`; raises if libogb200.so or a GPU is missing."""
+        Returns an `engine.DeviceProblem`; raises if libogb200.so or a GPU is missing.
+        jit=True also compiles the traced tapes into the sweep kernel (NVRTC)."""
         from . import engine, tape
         self._check_callbacks()
         ir = tape.build_ir(self, obj)
-        self._engine = engine.DeviceProblem(ir, self.bounds_arrays(), device or self.device)
+        self._engine = engine.DeviceProblem(ir, self.bounds_arrays(), device or self.device, jit=jit)
         return self._engine
 
     def evaluate_batch(self, P, obj=None, jacobian=True):
@@ -352,7 +353,7 @@ class Problem:
 
     def _device_callables(self, obj):
         """SciPy-facing closures whose values AND Jacobians come from the CUDA kernels."""
-        eng = self.compile(obj)
+        eng = self.compile(obj, jit=False)       # one instance per call: latency-bound, skip NVRTC
         meq, mineq, M = eng.meq, eng.mineq, eng.nrows
         memo = {"cx": None, "c": None, "jx": None, "jc": None, "J": None}
 

@@ -27,5 +27,7 @@ for backend in ("cuda", "host"):
     ceq = wo.prob.eval_equality(p.copy(), wo.obj)
     cin = wo.prob.eval_inequality(p.copy(), wo.obj)
     msgs = [l for l in buf.getvalue().splitlines() if "Current function value" in l or "Iterations" in l or "terminated" in l or "limit" in l]
+    if backend == "cuda":
+        print("device launches", wl.prob._engine.launches)
     print(backend, "time %.2fs" % dt, "h(tf)=%.7f" % wl.prob.states_all_section(0)[-1], "max|ceq|=%.2e" % np.abs(ceq).max(),
           "min cineq=%.2e" % cin.min(), msgs[-3:])
