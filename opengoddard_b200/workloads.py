@@ -614,3 +614,155 @@ def make_batch(wl, B, first=0, seed0=SEED0):
         P = wl.sanitize(prob, P)
     np.clip(P, lb, ub, out=P)
     return P
+
+
+# --------------------------------------------------------------------------
+# edge-case problems for the parity tests (not benchmark configs)
+# --------------------------------------------------------------------------
+def two_stage_no_inequality(api, nodes=(9, 11)):
+    """Two phases, linkage in the user equality, knot rows off, and an inequality function
+    that returns NO rows (reference examples/07_Rocket_Ascent_TwoStage.py:81-103 does that)."""
+    class Veh:
+        GMe, Re, g0 = 3.986004418e14, 6371.0e3, 9.80665
+        M0, M2, Mc, Cd, area, Isp = 5000, 2000, 0.4, 0.2, 10, 300.0
+
+    veh = Veh()
+    prob = api.Problem([0.0, 60.0, 150.0], list(nodes), [3, 3], [1, 1], 5)
+    prob.set_unit_states_all_section(0, veh.Re)
+    prob.set_unit_states_all_section(2, 1000.0)
+    prob.set_unit_time(100.0)
+
+    def dyn(prob, obj, section):
+        R = prob.states(0, section)
+        v = prob.states(1, section)
+        m = prob.states(2, section)
+        T = prob.controls(0, section)
+        rho = 1.225 * np.exp(-(R - obj.Re) / 8500.0)
+        drag = 0.5 * rho * v ** 2 * obj.Cd * obj.area
+        d = api.Dynamics(prob, section)
+        d[0] = v
+        d[1] = (T - drag) / m - obj.GMe / R ** 2
+        d[2] = - T / obj.g0 / obj.Isp
+        return d()
+
+    def eq(prob, obj):
+        R = prob.states_all_section(0)
+        v = prob.states_all_section(1)
+        m = prob.states_all_section(2)
+        r = api.Condition()
+        r.equal(R[0], obj.Re, unit=prob.unit_states[0][0])
+        r.equal(v[0], 0.0)
+        r.equal(m[0], obj.M0)
+        r.equal(m[-1], obj.M2 * obj.Mc)
+        r.equal(prob.states(0, 0)[-1], prob.states(0, 1)[0], unit=prob.unit_states[0][0])
+        r.equal(prob.states(1, 0)[-1], prob.states(1, 1)[0])
+        r.equal(prob.states(2, 0)[-1], prob.states(2, 1)[0] + 1200)
+        return r()
+
+    def ineq(prob, obj):
+        return api.Condition()()
+
+    def cost(prob, obj):
+        return -prob.states_all_section(0)[-1] / obj.Re
+
+    t = prob.time_all_section
+    prob.set_states_all_section(0, api.Guess.linear(t, veh.Re, veh.Re + 50e3))
+    prob.set_states_all_section(1, api.Guess.linear(t, 0.0, 900.0))
+    prob.set_states_all_section(2, api.Guess.linear(t, veh.M0, veh.M2 * veh.Mc))
+    prob.set_controls_all_section(0, api.Guess.constant(t, 1.2 * veh.M0 * veh.g0))
+    prob.set_controls_bounds_all_section(0, 0.0, 2.0 * veh.M0 * veh.g0)
+    prob.dynamics = [dyn, dyn]
+    prob.knot_states_smooth = [False]
+    prob.cost = cost
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("two_stage_no_inequality", prob, veh, None)
+
+
+def stress_mixed(api, nodes=(7, 33, 130)):
+    """Synthetic stress case: three phases of very different sizes (130 nodes > the 128 the
+    register-cached column code covers, so the generic code runs), a state-count change across
+    knot 0 (no knot rows there) and smooth-state rows at knot 1, a running cost, units, bounds on
+    states / controls / times, selects, several transcendental functions and a non-node-local row."""
+    class Par:
+        k1, k2, umax = 0.7, 1.3, 2.0
+
+    par = Par()
+    prob = api.Problem([0.0, 1.0, 2.5, 4.0], list(nodes), [2, 3, 3], [1, 2, 2], 3)
+    prob.set_unit_states_all_section(0, 2.0)
+    prob.set_unit_states(1, 1, 0.25)
+    prob.set_unit_controls_all_section(0, 4.0)
+    prob.set_unit_time(2.0)
+
+    def dyn(prob, obj, section):
+        x = prob.states(0, section)
+        y = prob.states(1, section)
+        u = prob.controls(0, section)
+        d = api.Dynamics(prob, section)
+        if section == 0:
+            d[0] = y + obj.k1 * np.sin(x)
+            d[1] = u - np.tanh(y) * x
+        else:
+            z = prob.states(2, section)
+            w = prob.controls(1, section)
+            sat = np.where(z > 0.5, 0.5 + 0.1 * (z - 0.5), z)
+            d[0] = y * np.cos(z) - obj.k2 * x / (1.0 + x ** 2)
+            d[1] = u - np.sqrt(1.0 + y ** 2) + np.abs(w)
+            d[2] = w * np.exp(-sat) - np.arctan2(y, 1.0 + x ** 2)
+        return d()
+
+    def eq(prob, obj):
+        r = api.Condition()
+        r.equal(prob.states(0, 0)[0], 0.3, unit=prob.unit_states[0][0])
+        r.equal(prob.states(1, 0)[0], -0.2)
+        r.equal(prob.states(0, 1)[0], prob.states(0, 0)[-1], unit=prob.unit_states[0][0])
+        r.equal(prob.states(1, 1)[0], prob.states(1, 0)[-1] * 1.5)
+        r.equal(prob.states(2, 1)[0], 0.1)
+        r.equal(prob.states(0, 2)[-1] ** 2 + prob.states(1, 2)[-1] ** 2, 1.0)
+        r.equal(prob.time_final(1) - prob.time_final(0), 1.4, unit=prob.unit_time)
+        return r()
+
+    def ineq(prob, obj):
+        u = prob.controls_all_section(0)
+        r = api.Condition()
+        r.lower_bound(u, -obj.umax, unit=prob.unit_controls[0][0])
+        r.upper_bound(u, obj.umax, unit=prob.unit_controls[0][0])
+        r.upper_bound(prob.controls(1, 2) ** 2 + prob.states(2, 2) ** 2, 9.0)
+        r.lower_bound(prob.states(0, 1)[2:-1], -5.0)
+        r.lower_bound(prob.time_final(0), 0.2)
+        r.upper_bound(prob.states(1, 0) - prob.states(1, 0)[0], 6.0)      # not node-local -> expanded
+        return r()
+
+    def cost(prob, obj):
+        return prob.time_final(-1) + 0.1 * prob.states(0, 2)[-1] ** 2
+
+    def running(prob, obj):
+        u = prob.controls_all_section(0)
+        x = prob.states_all_section(0)
+        return 0.5 * u ** 2 + 0.01 * np.cosh(0.1 * x)
+
+    t = prob.time_all_section
+    G = api.Guess
+    prob.set_states_all_section(0, G.cubic(t, 0.3, 0.1, 0.8, 0.0))
+    prob.set_states_all_section(1, G.linear(t, -0.2, 0.6))
+    for s in (1, 2):
+        prob.set_states(2, s, G.linear(prob.time[s], 0.1, 0.9))
+        prob.set_controls(1, s, G.constant(prob.time[s], 0.3))
+    prob.set_controls_all_section(0, G.linear(t, 0.5, -0.5))
+    prob.set_states_bounds_all_section(0, -3.0, 3.0)
+    prob.set_states_bounds(2, 2, 0.0, None)
+    prob.set_controls_bounds_all_section(0, -par.umax, par.umax)
+    prob.set_time_final_bounds(0, 0.2, 3.0)
+    prob.set_time_final_bounds(2, None, 9.0)
+    prob.dynamics = [dyn, dyn, dyn]
+    prob.knot_states_smooth = [True, True]       # knot 0 is skipped anyway: state counts differ
+    prob.cost = cost
+    prob.running_cost = running
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("stress_mixed", prob, par, None)
+
+
+CONFIGS["edge_two_stage_no_inequality"] = (two_stage_no_inequality, (9, 11))
+CONFIGS["edge_stress_mixed"] = (stress_mixed, (7, 33, 130))
+CONFIGS["edge_stress_small"] = (stress_mixed, (3, 4, 5))

@@ -10,7 +10,8 @@ from opengoddard_b200 import tape, workloads
 from tests.emu.emu import EmuProblem, binding
 from tests.helpers import (assert_c_close, assert_J_close, assert_lgl_close, golden, stacked_reference)
 
-CFGS = list(workloads.CONFIGS)
+CFGS = [k for k in workloads.CONFIGS if not k.startswith("edge_")]
+EDGE = [k for k in workloads.CONFIGS if k.startswith("edge_")]
 
 
 @pytest.mark.parametrize("N", [3, 4, 5, 8, 20, 25, 30, 40, 50, 64, 100, 128])
@@ -60,5 +61,23 @@ def test_bounds_drive_fd_steps(api):
     c, J = emu.eval_fd(P)
     for b in range(3):
         c_ref, J_ref = og_numpy.eval_fd(wo.prob, wo.obj, P[b], lb, ub)
+        assert_c_close(c[b], c_ref, J_ref, np.clip(P[b], lb, ub))
+        assert_J_close(J[b].T, J_ref)
+
+
+@pytest.mark.parametrize("name", EDGE)
+def test_edge_case_problems_vs_oracle(api, name):
+    """Empty inequality, 3..130 nodes per phase (130 > register-cached limit), state-count change
+    across a knot, smooth knot rows, running cost, selects, atan2/tanh/cosh/abs, non-local rows."""
+    from oracle import og_numpy
+    wl = workloads.build(name, api)
+    wo = workloads.build(name, og_numpy)
+    lb, ub = wl.prob.bounds_arrays()
+    emu = EmuProblem(tape.build_ir(wl.prob, wl.obj), lb, ub)
+    P = workloads.make_batch(wl, 2, first=3)
+    c, J = emu.eval_fd(P)
+    for b in range(2):
+        c_ref, J_ref = og_numpy.eval_fd(wo.prob, wo.obj, P[b], lb, ub)
+        assert emu.info.mineq == wo.prob.eval_inequality(P[b].copy(), wo.obj).size
         assert_c_close(c[b], c_ref, J_ref, np.clip(P[b], lb, ub))
         assert_J_close(J[b].T, J_ref)
