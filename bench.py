@@ -6,7 +6,8 @@
 
 One *step* = one pass of the hot path over one batch of synthetic instances: for every
 instance the stacked vector c = [c_eq; c_ineq; cost] and its dense forward-difference
-Jacobian (K1 D.X GEMM + K2 fused sweep).  One *eval* = one instance of one step.
+Jacobian (K1 D.X tensor-core GEMM + K2 fused sweep, the two launches ogb_eval_fd enqueues).
+One *eval* = one instance of one step.
 
 Default workload: the 4096-instance Goddard 50-node batch (north_star's headline; the
 batch=1024 case of BASELINE.json configs[1] is `--batch 1024`).  Weak scaling: every
@@ -282,7 +283,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     def step(timed):
-        """K1 then K2 on the current stream; returns (step event pair, sweep event pair)."""
+        """One pass of the hot path = what ogb_eval_fd enqueues: K1 (D.X tensor-core GEMM into the
+        scratch) then K2 (fused sweep), on the current stream; events around the step and K2."""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
         if timed:
             ev[0].record()

@@ -137,7 +137,10 @@ enum ogb_option {
     OGB_OPT_THREADS = 1,         /* CTA size of the sweep kernel: 64, 128, 192 or 256         */
     OGB_OPT_JIT = 2,             /* 1: run the NVRTC-specialised sweep kernel (tapes compiled to device
                                     code), 0: the ahead-of-time kernel with the tape interpreter       */
-    OGB_OPT_GRID_CAP = 3         /* cap on the persistent grid (0 = SM count x resident CTAs)         */
+    OGB_OPT_GRID_CAP = 3,        /* cap on the persistent grid (0 = SM count x resident CTAs)         */
+    OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
+                                    launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
+                                    (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */
 };
 int ogb_problem_set_option(void* prob, int key, int value);
 
@@ -158,7 +161,8 @@ int ogb_dx_gemm(void* prob, const double* p, const double* lb, const double* ub,
 
 /* K2 alone (ogb_eval / ogb_eval_fd = ogb_dx_gemm + ogb_sweep on one stream), exposed so the
  * dominant kernel can be timed and profiled by itself: DX must come from ogb_dx_gemm on the
- * same p and bounds.  J == NULL: constraint vector only (no clipping).                 */
+ * same p and bounds, or NULL to let the kernel compute D.X itself (OGB_OPT_FUSED_DX).
+ * J == NULL: constraint vector only (no clipping).                                      */
 int ogb_sweep(void* prob, const double* p, const double* DX, const double* lb, const double* ub,
               double abs_step, int B, double* c, double* J, void* stream);
 

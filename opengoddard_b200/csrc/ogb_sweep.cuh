@@ -48,6 +48,12 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// D = A(8x4, row) * B(4x8, col) + C, all FP64: one DMMA per warp
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // ------------------------------------------------------------------ K2: fused sweep
 // Persistent CTAs; one work item = (instance, group of <= G Jacobian columns).
 template <class T>
@@ -121,6 +127,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     const int n = P.n, M = P.M, ndx = P.ndx;
     const int nchunk = with_fd ? pl.split : 1;
     const long nitems = (long)B * nchunk;
+    const bool fused_dx = DX == nullptr;            // D.X by in-kernel DMMA instead of K1's scratch
     const size_t in_stride = pl.o_sdx - pl.o_sp + ((size_t)(ndx + 2 + 1) & ~(size_t)1);   // doubles per input stage
 
     // TMA bulk loads of p[b] and D.X[b] into input stage `st` (16-byte aligned body; an odd
@@ -128,10 +135,10 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     auto stage_inputs = [&](long item, int st) {
         const long b = item / nchunk;
         const double* gp = p + b * n;
-        const double* gdx = DX + b * ndx;
+        const double* gdx = fused_dx ? nullptr : DX + b * ndx;
         const int hp = (int)((reinterpret_cast<uintptr_t>(gp) >> 3) & 1);
         const int hd = (int)((reinterpret_cast<uintptr_t>(gdx) >> 3) & 1);
-        const int bp = (n - hp) & ~1, bd = (ndx - hd) & ~1;
+        const int bp = (n - hp) & ~1, bd = fused_dx ? 0 : (ndx - hd) & ~1;
         double* sp = smem + pl.o_sp + st * in_stride + hp;       // &sp[hp] is 16-byte aligned
         double* sdx = smem + pl.o_sdx + st * in_stride + hd;
         if (tid == 0) {
@@ -141,8 +148,10 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         } else if (tid == 32 % nthr) {
             if (hp) sp[0] = gp[0];
             for (int e = hp + bp; e < n; ++e) sp[e] = gp[e];
-            if (hd) sdx[0] = gdx[0];
-            for (int e = hd + bd; e < ndx; ++e) sdx[e] = gdx[e];
+            if (!fused_dx) {
+                if (hd) sdx[0] = gdx[0];
+                for (int e = hd + bd; e < ndx; ++e) sdx[e] = gdx[e];
+            }
         }
     };
 
@@ -163,7 +172,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         if (item + gridDim.x < nitems) stage_inputs(item + gridDim.x, st ^ 1);
         {
             const double* gp = p + b * n;
-            const double* gdx = DX + b * ndx;
+            const double* gdx = fused_dx ? nullptr : DX + b * ndx;
             W.sp = smem + pl.o_sp + st * in_stride + (int)((reinterpret_cast<uintptr_t>(gp) >> 3) & 1);
             W.sdx = smem + pl.o_sdx + st * in_stride + (int)((reinterpret_cast<uintptr_t>(gdx) >> 3) & 1);
         }
@@ -175,6 +184,44 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             }
         }
         __syncthreads();
+
+        // ---- phase 2a: D.X of this instance on the FP64 tensor cores (K1 fused in): per phase
+        //      OUT[a, i] = sum_l X[a, l] * D[i, l] as m8n8k4 DMMAs, A = the (clipped,
+        //      non-dimensional) states in shared memory, B = rows of D through the read-only
+        //      path; one (phase, 8 states, 8 nodes) tile per warp at a time; same k order as K1,
+        //      so the result is bit-identical to ogb_dx_gemm.
+        if (fused_dx) {
+            const int qr = lane >> 2, qc = lane & 3;
+            int unit0 = 0;
+            for (int s = 0; s < P.nsec; ++s) {
+                const OgbSec& S = P.sec[s];
+                const int N = S.N, Kp = (N + 3) & ~3;
+                const int mt = (S.ns + 7) >> 3, nt = (N + 7) >> 3;
+                const double* __restrict__ Dm = P.D + S.doff;
+                for (int u = warp - unit0 % nwarps; u < mt * nt; u += nwarps) {
+                    if (u < 0) continue;
+                    const int a = (u / nt) * 8 + qr, i0 = (u % nt) * 8;
+                    const bool av_ok = a < S.ns;
+                    const double un = av_ok ? P.ustate[S.us_off + a] : 1.0;
+                    const double* xs = W.sp + S.off + a * N;
+                    const double* brow = Dm + (i0 + qr) * N;
+                    const bool b_ok = i0 + qr < N;
+                    double acc0 = 0.0, acc1 = 0.0;
+                    for (int l0 = 0; l0 < Kp; l0 += 4) {
+                        const int l = l0 + qc;
+                        const double av = (av_ok && l < N) ? ogb_nd(xs[l], un) : 0.0;
+                        const double bv = (b_ok && l < N) ? __ldg(brow + l) : 0.0;
+                        dmma_8x8x4(acc0, acc1, av, bv);
+                    }
+                    const int ar = (u / nt) * 8 + qr, i = i0 + 2 * qc;
+                    if (ar < S.ns) {
+                        if (i < N) W.sdx[S.dxoff + ar * N + i] = acc0;
+                        if (i + 1 < N) W.sdx[S.dxoff + ar * N + i + 1] = acc1;
+                    }
+                }
+                unit0 += mt * nt;
+            }
+        }
 
         // ---- phase 2: tapes -- base nodes, scalar program, one job per Jacobian column
         for (int q = tid; q < P.gtot + 1 + ncols; q += nthr) ogb_job(P, W, q, jlo, lb, ub, abs_step);

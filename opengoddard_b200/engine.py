@@ -50,6 +50,7 @@ class DeviceProblem:
         self._work = None
         self._one = None
         self.launches = 0                         # kernels launched through this handle
+        self.fused_dx = False                     # ogb_eval / ogb_eval_fd = K1 + K2 (option 4 fuses them)
         mode = os.environ.get("OGB200_JIT", "")
         self.jit_error = None
         if mode != "0" and (jit or mode == "require"):
@@ -73,8 +74,11 @@ class DeviceProblem:
 
     # ------------------------------------------------------------------ helpers
     def set_option(self, key, value):
-        """ogb_problem_set_option (include/ogb200.h): 0 generic columns, 1 threads, 3 grid cap."""
+        """ogb_problem_set_option (include/ogb200.h): 0 generic columns, 1 threads, 2 jit,
+        3 grid cap, 4 fused D.X."""
         self._rc(self.b.lib.ogb_problem_set_option(self.h, int(key), int(value)), "ogb_problem_set_option")
+        if int(key) == 4:
+            self.fused_dx = bool(value)
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -136,7 +140,7 @@ class DeviceProblem:
         with t.cuda.device(self.device):
             self._rc(self.b.lib.ogb_eval(self.h, P.data_ptr(), B, c.data_ptr(), work.data_ptr(),
                                          self._stream()), "ogb_eval")
-        self.launches += 2
+        self.launches += 1 if self.fused_dx else 2
         return c
 
     def eval_fd(self, P, out_c=None, out_J=None, abs_step=ABS_STEP):
@@ -152,7 +156,7 @@ class DeviceProblem:
             self._rc(self.b.lib.ogb_eval_fd(self.h, P.data_ptr(), self.lb.data_ptr(), self.ub.data_ptr(),
                                             float(abs_step), B, c.data_ptr(), J.data_ptr(),
                                             work.data_ptr(), self._stream()), "ogb_eval_fd")
-        self.launches += 2
+        self.launches += 1 if self.fused_dx else 2
         return c, J
 
     # ------------------------------------------------------------------ single-instance host API

@@ -60,6 +60,9 @@ def test_jit_and_interpreter_kernels_agree(torch_cuda, api, name):
     c0, J0 = eng.eval_fd(P)
     e0 = eng.eval(P)
     assert torch_cuda.equal(c0, c1) and torch_cuda.equal(J0, J1) and torch_cuda.equal(e0, e1)
+    eng.set_option(4, 1)                      # one launch: D.X by DMMA inside the sweep kernel
+    c2, J2 = eng.eval_fd(P)
+    assert torch_cuda.equal(c2, c1) and torch_cuda.equal(J2, J1)
 
 
 @pytest.mark.parametrize("name", ["cfg2_goddard50", "cfg3_goddard_knot30x2"])
@@ -131,6 +134,11 @@ def test_full_size_properties(torch_cuda, api):
     cg, Jg = eng.eval_fd(P[:300])
     eng.set_option(0, 0)
     assert torch_cuda.equal(cg, c[:300]) and torch_cuda.equal(Jg, J[:300])
+    # D.X computed inside the sweep kernel (option 4) == K1 (ogb_dx_gemm) + scratch, bit for bit
+    eng.set_option(4, 1)
+    cu, Ju = eng.eval_fd(P[:300])
+    eng.set_option(4, 0)
+    assert torch_cuda.equal(cu, c[:300]) and torch_cuda.equal(Ju, J[:300])
     # the NVRTC-compiled tapes and the tape interpreter agree bit for bit
     assert eng.info.jit == 1, "NVRTC specialisation did not engage on the GPU box"
     eng.set_option(2, 0)
