@@ -10,6 +10,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +42,14 @@ static inline size_t ogb_even(size_t x) { return (x + 1) & ~(size_t)1; }
 //   descriptor cache | 2 input stages (p, D.X) | base outputs | c | scalar outs | coef |
 //   prefix | perturbed outputs [max_nouts][G] | dx, x1, dlt, cost [G] | column records [G] |
 //   scalar perturbed outs | cf | rterm | slot table |
+// resident threads per SM the sweep kernel's register budget allows (3 x 256 by default;
+// OGB200_JIT_MINBLOCKS = 4 rebuilds the NVRTC kernel for 64 registers -> 4 x 256)
+static inline int ogb_thread_budget() {
+    const char* mb = getenv("OGB200_JIT_MINBLOCKS");
+    const int k = mb ? atoi(mb) : 3;
+    return 256 * (k >= 1 && k <= 8 ? k : 3);
+}
+
 static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, size_t nouts, int warps,
                               OgbPlan* pl) {
     size_t o = 0;
@@ -89,7 +98,7 @@ static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts,
         ogb_layout(P, ncode, nconsts, nouts, w, pl);
         if (pl->smem_bytes > SMEM_MAX) continue;
         int ctas = (int)std::min<size_t>(16, SM_SMEM / (pl->smem_bytes + 1024));
-        ctas = std::min(ctas, 768 / (w * 32));
+        ctas = std::min(ctas, ogb_thread_budget() / (w * 32));
         if (ctas < 1) continue;
         const int res = ctas * w;
         if (res > best_res) { best_res = res; best_w = w; }
@@ -103,7 +112,7 @@ static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts,
         return false;
     }
     ogb_layout(P, ncode, nconsts, nouts, best_w, pl);
-    pl->ctas_per_sm = std::max(1, std::min((int)(SM_SMEM / (pl->smem_bytes + 1024)), 768 / pl->threads));
+    pl->ctas_per_sm = std::max(1, std::min((int)(SM_SMEM / (pl->smem_bytes + 1024)), ogb_thread_budget() / pl->threads));
     return true;
 }
 

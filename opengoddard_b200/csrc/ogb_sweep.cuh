@@ -72,8 +72,11 @@ struct OgbSlot { int rbase, klo, khi, isdyn; };   // where output slot t of a no
 #define OGB_FAST_MAXN 128      // register-cached row constants cover phases up to 128 nodes
 
 // NR = ceil(max nodes per phase / 32): row constants held per lane (0 = generic column code only)
+#ifndef OGB_MIN_BLOCKS
+#define OGB_MIN_BLOCKS 3            // resident CTAs per SM the register budget is sized for
+#endif
 template <int NR>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, OGB_MIN_BLOCKS)
 ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const double* __restrict__ DX,
                  const double* __restrict__ lb, const double* __restrict__ ub, double abs_step,
                  int B, double* __restrict__ c, double* __restrict__ J, int with_fd,
