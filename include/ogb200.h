@@ -50,7 +50,8 @@ enum ogb_opcode {
     OGB_ASIN = 29, OGB_ACOS = 30, OGB_ATAN = 31, OGB_SINH = 32, OGB_COSH = 33,
     OGB_TANH = 34, OGB_LOG10 = 35, OGB_SIGN = 36, OGB_FLOOR = 37, OGB_CEIL = 38,
     OGB_AND = 39, OGB_OR = 40, OGB_NOT = 41,
-    OGB_OP_COUNT = 42
+    OGB_INTERP = 42, /* r[dst] = table b evaluated at r[a] (scipy.interpolate.interp1d, linear)  */
+    OGB_OP_COUNT = 43
 };
 #define OGB_MAX_REG 96      /* registers per tape (host compiler enforces)   */
 #define OGB_MAX_FIELD 16383 /* 14-bit operand fields                         */
@@ -73,6 +74,19 @@ typedef struct ogb_out {
     int32_t row;
     int32_t glo, ghi;       /* global node range (over concatenated phases) for *_POINT kinds  */
 } ogb_out;
+
+/* A 1-D linear lookup table traced from a `scipy.interpolate.interp1d(x, y)` object called
+ * inside a callback (reference examples/11_Polar_TSTO_Taiki.py:21-27,94-98).  variant 0 = the
+ * np.interp formula SciPy uses for float tables that do not extrapolate
+ * (slope*(x - x_lo) + y_lo), variant 1 = SciPy's two-term formula
+ * ((x-x_lo)/(x_hi-x_lo)*y_hi + (x_hi-x)/(x_hi-x_lo)*y_lo, used with fill_value="extrapolate").
+ * Without extrapolation x below / above the table yields fill_below / fill_above (NaN where the
+ * reference would raise because bounds_error is set).                                        */
+typedef struct ogb_table {
+    int32_t off, len;        /* slice of table_x_h / table_y_h (x ascending)                    */
+    int32_t variant, extrapolate;
+    double fill_below, fill_above;
+} ogb_table;
 
 typedef struct ogb_program {
     const uint64_t* code_h;   int32_t ncode;
@@ -97,6 +111,10 @@ typedef struct ogb_problem_desc {
     int32_t has_running_cost;
     const ogb_program* node_prog_h;   /* [nsec] one node program per phase            */
     const ogb_program* scalar_prog_h; /* exactly one (may have ncode == 0 outs == 0)  */
+    int32_t ntables;                  /* lookup tables referenced by OGB_INTERP       */
+    const ogb_table* tables_h;        /* [ntables]                                    */
+    const double* table_x_h;          /* concatenated abscissae                       */
+    const double* table_y_h;          /* concatenated ordinates                       */
 } ogb_problem_desc;
 
 typedef struct ogb_problem_info {

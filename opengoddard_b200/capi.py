@@ -25,6 +25,11 @@ class OgbProgram(C.Structure):
                 ("nreg", C.c_int32)]
 
 
+class OgbTable(C.Structure):
+    _fields_ = [("off", C.c_int32), ("len", C.c_int32), ("variant", C.c_int32), ("extrapolate", C.c_int32),
+                ("fill_below", C.c_double), ("fill_above", C.c_double)]
+
+
 class OgbProblemDesc(C.Structure):
     _fields_ = [("nsec", C.c_int32),
                 ("nodes_h", C.POINTER(C.c_int32)),
@@ -38,7 +43,11 @@ class OgbProblemDesc(C.Structure):
                 ("mineq_user", C.c_int32),
                 ("has_running_cost", C.c_int32),
                 ("node_prog_h", C.POINTER(OgbProgram)),
-                ("scalar_prog_h", C.POINTER(OgbProgram))]
+                ("scalar_prog_h", C.POINTER(OgbProgram)),
+                ("ntables", C.c_int32),
+                ("tables_h", C.POINTER(OgbTable)),
+                ("table_x_h", C.POINTER(C.c_double)),
+                ("table_y_h", C.POINTER(C.c_double))]
 
 
 class OgbProblemInfo(C.Structure):
@@ -74,12 +83,22 @@ def make_desc(ir):
     progs = (OgbProgram * len(ir.node_tapes))(*[_program(t, keep) for t in ir.node_tapes])
     scalar = (OgbProgram * 1)(_program(ir.scalar_tape, keep))
     keep.extend([progs, scalar])
+    tabs = (OgbTable * max(1, len(ir.tables)))()
+    tx, ty, off = [], [], 0
+    for i, t in enumerate(ir.tables):
+        tabs[i] = OgbTable(off, len(t["x"]), int(t["variant"]), 1 if t["extrapolate"] else 0,
+                           float(t["fill_below"]), float(t["fill_above"]))
+        tx.extend(np.asarray(t["x"], dtype=float).tolist())
+        ty.extend(np.asarray(t["y"], dtype=float).tolist())
+        off += len(t["x"])
+    keep.append(tabs)
     desc = OgbProblemDesc(
         len(ir.nodes), arr(ir.nodes, C.c_int32, np.int32), arr(ir.nstates, C.c_int32, np.int32),
         arr(ir.ncontrols, C.c_int32, np.int32), arr(ir.unit_states, C.c_double, np.float64),
         float(ir.unit_time), float(ir.t0),
         arr([1 if k else 0 for k in ir.knot_smooth], C.c_uint8, np.uint8),
-        int(ir.meq_user), int(ir.mineq_user), 1 if ir.has_running_cost else 0, progs, scalar)
+        int(ir.meq_user), int(ir.mineq_user), 1 if ir.has_running_cost else 0, progs, scalar,
+        len(ir.tables), tabs, arr(tx, C.c_double, np.float64), arr(ty, C.c_double, np.float64))
     return desc, keep
 
 

@@ -74,6 +74,9 @@ struct OgbProb {
     const OgbKnot* knots;
     const OgbCol* cols;
     const int* pickvars;
+    const ogb_table* tables;    // lookup tables of OGB_INTERP
+    const double* tab_x;
+    const double* tab_y;
 };
 
 struct OgbWork {            // per work item scratch (shared memory on the device)
@@ -194,8 +197,55 @@ struct OgbScalarLoad {      // scalar program input: variable `a` of p
     OGB_HD double operator()(int a) const { return a == pvar ? x1 : sp[a]; }
 };
 
+// scipy.interpolate.interp1d (kind='linear') at one point, reproducing SciPy's arithmetic:
+// variant 0: interp1d._call_linear_np = numpy.interp (compiled_base.c arr_interp), variant 1:
+// interp1d._call_linear; then interp1d._evaluate's out-of-range fill unless extrapolating.
+OGB_HD double ogb_interp(const OgbProb& P, int id, double x) {
+    const ogb_table T = P.tables[id];
+    const double* xp = P.tab_x + T.off;
+    const double* fp = P.tab_y + T.off;
+    const int n = T.len;
+    double y;
+    if (T.variant == 0) {
+        if (x > xp[n - 1]) y = fp[n - 1];
+        else if (x < xp[0]) y = fp[0];
+        else if (!(x == x)) y = x;
+        else {
+            int lo = 0, hi = n - 1;                 // last j with xp[j] <= x
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (xp[mid] <= x) lo = mid; else hi = mid - 1;
+            }
+            const int j = lo;
+            if (j == n - 1 || xp[j] == x) y = fp[j];
+            else {
+                const double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+                y = slope * (x - xp[j]) + fp[j];
+                if (!(y == y)) {
+                    y = slope * (x - xp[j + 1]) + fp[j + 1];
+                    if (!(y == y) && fp[j] == fp[j + 1]) y = fp[j];
+                }
+            }
+        }
+    } else {
+        int lo = 0, hi = n;                         // searchsorted(side='left'): first i with xp[i] >= x
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (xp[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        int i = lo < 1 ? 1 : (lo > n - 1 ? n - 1 : lo);
+        const double x_lo = xp[i - 1], x_hi = xp[i];
+        y = ((x - x_lo) / (x_hi - x_lo)) * fp[i] + ((x_hi - x) / (x_hi - x_lo)) * fp[i - 1];
+    }
+    if (!T.extrapolate) {
+        if (x < xp[0]) y = T.fill_below;
+        if (x > xp[n - 1]) y = T.fill_above;
+    }
+    return y;
+}
+
 template <class Load>
-OGB_HD void ogb_run_tape(const uint64_t* code, int ncode, const double* consts,
+OGB_HD void ogb_run_tape(const OgbProb& P, const uint64_t* code, int ncode, const double* consts,
                          const Load& ld, double* out, int ostride) {
     double r[OGB_MAX_REG];
     for (int pc = 0; pc < ncode; ++pc) {
@@ -248,6 +298,7 @@ OGB_HD void ogb_run_tape(const uint64_t* code, int ncode, const double* consts,
             case OGB_AND: v = (r[a] != 0.0 && r[b] != 0.0) ? 1.0 : 0.0; break;
             case OGB_OR: v = (r[a] != 0.0 || r[b] != 0.0) ? 1.0 : 0.0; break;
             case OGB_NOT: v = (r[a] == 0.0) ? 1.0 : 0.0; break;
+            case OGB_INTERP: v = ogb_interp(P, b, r[a]); break;
             default: continue;
         }
         r[d] = v;
@@ -294,16 +345,16 @@ OGB_HD void ogb_dx_row(const OgbProb& P, const OgbSec& S, int a, const double* p
 // generated from the same tapes (ogb_jit_node / ogb_jit_scalar are emitted by ogb_kernels.cu).
 #ifdef OGB_JIT
 template <class Load>
-__device__ __forceinline__ void ogb_jit_node(int sec, const Load& ld, double* out, int ostride);
+__device__ __forceinline__ void ogb_jit_node(const OgbProb& P, int sec, const Load& ld, double* out, int ostride);
 template <class Load>
-__device__ __forceinline__ void ogb_jit_scalar(const Load& ld, double* out, int ostride);
-#define OGB_NODE_PROGRAM(s, S, ld, out, stride) ogb_jit_node((s), (ld), (out), (stride))
-#define OGB_SCALAR_PROGRAM(ld, out, stride) ogb_jit_scalar((ld), (out), (stride))
+__device__ __forceinline__ void ogb_jit_scalar(const OgbProb& P, const Load& ld, double* out, int ostride);
+#define OGB_NODE_PROGRAM(s, S, ld, out, stride) ogb_jit_node(P, (s), (ld), (out), (stride))
+#define OGB_SCALAR_PROGRAM(ld, out, stride) ogb_jit_scalar(P, (ld), (out), (stride))
 #else
 #define OGB_NODE_PROGRAM(s, S, ld, out, stride) \
-    ogb_run_tape(P.code + (S).code_off, (S).ncode, P.consts + (S).const_off, (ld), (out), (stride))
+    ogb_run_tape(P, P.code + (S).code_off, (S).ncode, P.consts + (S).const_off, (ld), (out), (stride))
 #define OGB_SCALAR_PROGRAM(ld, out, stride) \
-    ogb_run_tape(P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, (ld), (out), (stride))
+    ogb_run_tape(P, P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, (ld), (out), (stride))
 #endif
 
 // ------------------------------------------------------------------ phase 2: tape jobs

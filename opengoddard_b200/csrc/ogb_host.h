@@ -25,6 +25,8 @@ struct OgbHostProblem {
     std::vector<OgbKnot> knots;
     std::vector<OgbCol> cols;
     std::vector<int> pickvars;
+    std::vector<ogb_table> tables;
+    std::vector<double> tab_x, tab_y;
     OgbProb P;          // pointer members reference the vectors above (host view)
     OgbPlan plan;
     std::string error;
@@ -33,6 +35,7 @@ struct OgbHostProblem {
         P.sec = sec.data(); P.outs = outs.data(); P.code = code.data(); P.consts = consts.data();
         P.D = D.data(); P.Dt = Dt.data(); P.w = w.data(); P.ustate = ustate.data();
         P.knots = knots.data(); P.cols = cols.data(); P.pickvars = pickvars.data();
+        P.tables = tables.data(); P.tab_x = tab_x.data(); P.tab_y = tab_y.data();
     }
 };
 
@@ -188,6 +191,18 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
     P.M = P.meq + P.mineq + 1;
     if ((double)P.n * (double)P.M >= 4.0e9) { delete H; return fail("Jacobian of one instance exceeds 2^32 entries"); }
 
+    // ---- lookup tables
+    for (int t = 0; t < d->ntables; ++t) {
+        const ogb_table T = d->tables_h[t];
+        if (T.len < 2 || T.off < 0) { delete H; return fail("bad lookup table"); }
+        for (int k = 1; k < T.len; ++k)
+            if (!(d->table_x_h[T.off + k] >= d->table_x_h[T.off + k - 1])) { delete H; return fail("lookup table abscissae must ascend"); }
+        H->tables.push_back(T);
+        const int end = T.off + T.len;
+        if ((int)H->tab_x.size() < end) { H->tab_x.resize(end); H->tab_y.resize(end); }
+        for (int k = T.off; k < end; ++k) { H->tab_x[k] = d->table_x_h[k]; H->tab_y[k] = d->table_y_h[k]; }
+    }
+    const int ntables = d->ntables;
     // ---- tapes
     auto add_prog = [&](const ogb_program& pr, int* code_off, int* const_off, int* out_off) -> bool {
         if (pr.nreg > OGB_MAX_REG) { *err = "tape needs more than OGB_MAX_REG registers"; return false; }
@@ -223,6 +238,7 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
             if (op == OGB_OUT && dd >= pr.nouts) { *err = "tape OUT slot out of range"; return false; }
             if (op == OGB_LDC && aa >= pr.nconsts) { *err = "tape constant index out of range"; return false; }
             if (op != OGB_OUT && op != OGB_NOP && dd >= pr.nreg) { *err = "tape register out of range"; return false; }
+            if (op == OGB_INTERP && (int)((ins >> 14) & 0x3fff) >= ntables) { *err = "tape references a missing lookup table"; return false; }
         }
         return true;
     };

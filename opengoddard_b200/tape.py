@@ -19,7 +19,7 @@ OPCODES = {
     "sel": 18, "neg": 19, "sqrt": 20, "exp": 21, "log": 22, "sin": 23, "cos": 24, "tan": 25,
     "abs": 26, "square": 27, "recip": 28, "asin": 29, "acos": 30, "atan": 31, "sinh": 32,
     "cosh": 33, "tanh": 34, "log10": 35, "sign": 36, "floor": 37, "ceil": 38, "and": 39,
-    "or": 40, "not": 41,
+    "or": 40, "not": 41, "interp": 42,
 }
 MAX_REG = 96
 MAX_FIELD = 16383
@@ -95,6 +95,8 @@ def compile_tape(out_nodes, outs, leaf_arg):
             code.append(_word(OPCODES["ldc"], d, cindex[key]))
         elif n.op in ("blk", "var"):
             code.append(_word(OPCODES["ldp"], d, leaf_arg(n)))
+        elif n.op == "interp":
+            code.append(_word(OPCODES["interp"], d, srcs[0], int(n.value)))
         else:
             s = srcs + [0] * (3 - len(srcs))
             code.append(_word(OPCODES[n.op], d, s[0], s[1], s[2]))
@@ -123,6 +125,7 @@ class ProblemIR:
     node_tapes: list            # one Tape per phase
     scalar_tape: Tape
     nvars: int = 0
+    tables: list = field(default_factory=list)   # dicts: x, y, variant, extrapolate, fill_below, fill_above
     meta: dict = field(default_factory=dict)
 
 
@@ -165,6 +168,12 @@ class _RowBuilder:
 
 
 def build_ir(prob, obj):
+    """Trace every callback of `prob` once and return the ProblemIR (see _build_ir)."""
+    with T.interp1d_tracing():
+        return _build_ir(prob, obj)
+
+
+def _build_ir(prob, obj):
     """Trace every callback of `prob` once and return the ProblemIR.
     Row order = the reference's: user equality rows, defects per phase/state/node, knot
     rows, user inequality rows, cost (optimize.py:670-698, :723-728)."""
@@ -269,4 +278,5 @@ def build_ir(prob, obj):
         knot_smooth=[bool(smooth[k]) for k in range(nsec - 1)],
         meq_user=eq.nrows, mineq_user=ineq.nrows, has_running_cost=run_parts is not None,
         node_tapes=node_tapes, scalar_tape=scalar_tape, nvars=ctx.nvars,
+        tables=[{k: v for k, v in t.items() if k != "keep"} for t in ctx.tables],
         meta={"graph_nodes": len(g.nodes)})

@@ -89,6 +89,10 @@ class Graph:
                 return a
         return self._intern(name, args)
 
+    def interp(self, table_id, x):
+        """linear lookup table `table_id` (see TraceContext.table_of) evaluated at node x"""
+        return self._intern("interp", (x,), float(table_id))
+
 
 def substitute_blocks(graph, node, fn, memo):
     """Rebuild `node` with every ('blk', s, b) leaf replaced by fn(s, b)."""
@@ -99,6 +103,8 @@ def substitute_blocks(graph, node, fn, memo):
         out = fn(*node.args)
     elif node.op in ("const", "var"):
         out = node
+    elif node.op == "interp":
+        out = graph.interp(int(node.value), substitute_blocks(graph, node.args[0], fn, memo))
     else:
         out = graph.op(node.op, *[substitute_blocks(graph, a, fn, memo) for a in node.args])
     memo[node.uid] = out
@@ -143,6 +149,31 @@ class TraceContext:
             g += self.nodes[s]
         self.gtot = g
         self.nvars = o + self.nsec
+        self.tables = []              # lookup tables met while tracing: dicts x, y, variant, ...
+        self._table_ids = {}
+
+    def table_of(self, f):
+        """Register a scipy.interpolate.interp1d object; returns its table id."""
+        key = id(f)
+        if key in self._table_ids:
+            return self._table_ids[key]
+        kind = getattr(f, "_kind", None)
+        call = getattr(getattr(f, "_call", None), "__name__", "")
+        y = np.asarray(f.y, dtype=float)
+        if kind != "linear" or y.ndim != 1 or call not in ("_call_linear_np", "_call_linear"):
+            raise TraceError("only 1-D linear scipy.interpolate.interp1d tables can be compiled for the "
+                             "device (got kind=%r, y.ndim=%d)" % (kind, y.ndim))
+        extrap = bool(getattr(f, "_extrapolate", False))
+        nan = float("nan")
+        below = above = nan
+        if not extrap and not f.bounds_error:
+            below = float(np.asarray(f._fill_value_below, dtype=float).ravel()[0])
+            above = float(np.asarray(f._fill_value_above, dtype=float).ravel()[0])
+        self.tables.append(dict(x=np.asarray(f.x, dtype=float).copy(), y=y.copy(),
+                                variant=0 if call == "_call_linear_np" else 1, extrapolate=extrap,
+                                fill_below=below, fill_above=above, keep=f))
+        self._table_ids[key] = len(self.tables) - 1
+        return self._table_ids[key]
 
     def section_of(self, g):
         for s in range(self.nsec - 1, -1, -1):
@@ -286,6 +317,13 @@ class Sym:
         if a.rng is None:
             return Sym(self.ctx, vec.rng, {s: g.op(name, a.parts, p) for s, p in vec.parts.items()})
         return Sym(self.ctx, vec.rng, {s: g.op(name, p, b.parts) for s, p in vec.parts.items()})
+
+    def _interp(self, f):
+        """this value pushed through the scipy interp1d object `f`"""
+        g, tid = self.ctx.graph, self.ctx.table_of(f)
+        if self.rng is None:
+            return Sym(self.ctx, None, g.interp(tid, self.parts))
+        return Sym(self.ctx, self.rng, {s: g.interp(tid, p) for s, p in self.parts.items()})
 
     def _un(self, name):
         g = self.ctx.graph
@@ -588,6 +626,32 @@ class TraceView:
 
     def time_final_all_section(self):
         return [self.time_final(s) for s in range(self._ctx.nsec)]
+
+
+class interp1d_tracing:
+    """While callbacks are being traced, calling a `scipy.interpolate.interp1d` object with a
+    traced value records a table lookup instead of evaluating (reference
+    examples/11_Polar_TSTO_Taiki.py:94-98 does `obj.airDensity(R - obj.Re)`)."""
+
+    def __enter__(self):
+        from scipy.interpolate import interp1d
+        self.cls = interp1d
+        self.orig = interp1d.__call__
+        orig = self.orig
+
+        def call(f, x):
+            if isinstance(x, Sym):
+                return x._interp(f)
+            if isinstance(x, SymList):
+                return SymList([e._interp(f) if isinstance(e, Sym) else orig(f, e) for e in x.items])
+            return orig(f, x)
+
+        interp1d.__call__ = call
+        return self
+
+    def __exit__(self, *exc):
+        self.cls.__call__ = self.orig
+        return False
 
 
 class SymRows:

@@ -766,3 +766,78 @@ def stress_mixed(api, nodes=(7, 33, 130)):
 CONFIGS["edge_two_stage_no_inequality"] = (two_stage_no_inequality, (9, 11))
 CONFIGS["edge_stress_mixed"] = (stress_mixed, (7, 33, 130))
 CONFIGS["edge_stress_small"] = (stress_mixed, (3, 4, 5))
+
+
+def table_lookup(api, nodes=(12, 9)):
+    """Edge case: data tables (`scipy.interpolate.interp1d`) inside the callbacks, the way
+    reference examples/11_Polar_TSTO_Taiki.py:21-27,94-98 uses them: a float table with constant
+    fill outside its range (SciPy takes the numpy.interp path), one with fill_value="extrapolate"
+    (SciPy's two-term formula) and one with NaN fill that is only used in range."""
+    from scipy import interpolate
+
+    class Air:
+        alt = np.array([0.0, 1.0, 2.5, 4.0, 7.0, 11.0, 15.0, 20.0, 32.0, 47.0])
+        rho = np.array([1.225, 1.112, 0.957, 0.819, 0.590, 0.365, 0.194, 0.0880, 0.0132, 0.00143])
+        snd = np.array([340.3, 336.4, 330.6, 324.6, 312.3, 295.1, 295.1, 295.1, 303.0, 329.8])
+        mach = np.array([0.0, 0.4, 0.8, 1.0, 1.2, 2.0, 4.0])
+        cd = np.array([0.30, 0.31, 0.38, 0.55, 0.62, 0.45, 0.33])
+        density = interpolate.interp1d(alt, rho, bounds_error=False, fill_value=(rho[0], 0.0))
+        sound = interpolate.interp1d(alt, snd, bounds_error=False, fill_value=(snd[0], snd[-1]))
+        drag = interpolate.interp1d(mach, cd, fill_value="extrapolate")
+        gain = interpolate.interp1d(np.array([-10.0, 0.0, 10.0, 60.0]), np.array([0.5, 1.0, 1.5, 1.2]))
+        g0 = 9.80665e-3          # km / s^2
+
+    air = Air()
+    prob = api.Problem([0.0, 40.0, 120.0], list(nodes), [3, 3], [1, 1], 5)
+    prob.set_unit_states_all_section(1, 0.5)
+    prob.set_unit_time(50.0)
+
+    def dyn(prob, obj, section):
+        h = prob.states(0, section)          # km
+        v = prob.states(1, section)          # km/s
+        m = prob.states(2, section)
+        T = prob.controls(0, section)
+        mach = np.sqrt(v ** 2) * 1000.0 / obj.sound(h)
+        q = 0.5 * obj.density(h) * (v * 1000.0) ** 2
+        d = api.Dynamics(prob, section)
+        d[0] = v
+        d[1] = (T * obj.gain(h) - 1e-6 * q * obj.drag(mach)) / m - obj.g0
+        d[2] = -T / (2.5 + 0.1 * section)
+        return d()
+
+    def eq(prob, obj):
+        r = api.Condition()
+        r.equal(prob.states(0, 0)[0], 0.0)
+        r.equal(prob.states(1, 0)[0], 0.05)
+        r.equal(prob.states(2, 0)[0], 1.0)
+        r.equal(obj.density(prob.states(0, 1)[-1]), 0.02)        # a table inside a scalar row
+        return r()
+
+    def ineq(prob, obj):
+        h = prob.states_all_section(0)
+        v = prob.states_all_section(1)
+        r = api.Condition()
+        r.upper_bound(0.5 * obj.density(h) * (v * 1000.0) ** 2, 60000.0, unit=1000.0)
+        r.lower_bound(prob.states_all_section(2), 0.2)
+        return r()
+
+    def cost(prob, obj):
+        return -prob.states(2, 1)[-1]
+
+    t = prob.time_all_section
+    G = api.Guess
+    prob.set_states_all_section(0, G.cubic(t, 0.0, 0.05, 55.0, 0.3))     # leaves the 0..47 km table range
+    prob.set_states_all_section(1, G.linear(t, 0.05, 1.4))
+    prob.set_states_all_section(2, G.linear(t, 1.0, 0.35))
+    prob.set_controls_all_section(0, G.linear(t, 0.03, 0.005))
+    prob.set_states_bounds_all_section(0, -5.0, None)
+    prob.set_controls_bounds_all_section(0, 0.0, 0.05)
+    prob.dynamics = [dyn, dyn]
+    prob.knot_states_smooth = [True]
+    prob.cost = cost
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("table_lookup", prob, air, None)
+
+
+CONFIGS["edge_table_lookup"] = (table_lookup, (12, 9))

@@ -35,7 +35,7 @@ from oracle import ref_loader  # noqa: E402
 ABS_STEP = float(np.sqrt(np.finfo(np.float64).eps))   # scipy/optimize/_slsqp_py.py:34
 
 LGL_NODES = (3, 4, 5, 8, 20, 25, 30, 40, 50, 64, 100, 128)
-EXAMPLES_FD = ("01", "04", "05", "09", "10")
+EXAMPLES_FD = ("01", "04", "05", "09", "10", "11")
 EXAMPLES_C = ("02", "03", "06", "07", "08")
 WORKLOAD_INSTANCES = {
     "cfg1_brachistochrone20": 3,
