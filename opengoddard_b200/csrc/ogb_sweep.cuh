@@ -255,27 +255,42 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         {
             constexpr int NRA = NR > 0 ? NR : 1;
             double* __restrict__ Jb = J + (size_t)b * n * (size_t)M;   // n * M < 2^32 (checked on the host)
-            int cur_sec = -1, cur_blk = -1;
+            int cur_sec = -1, cur_blk = -1, slot_sec = -1;
             double r_sdx[NRA], r_cf[NRA], r_sc[NRA];
+            OgbSlot si = {0, 0, 0, 0};               // where this lane's output slot lands (per phase)
+            // Everything a column needs from shared / read-only memory is fetched one column ahead
+            // (software pipeline), so the loads of column c+1 fly while column c streams out.
+            struct ColMeta { OgbCol cd; double dx, rdx, dlt, x1, dkk, pv; double dtv[NRA]; };
+            auto load_meta = [&](int cc, ColMeta& m) {
+                m.cd = W.pcol[cc]; m.dx = W.pdx[cc]; m.rdx = W.prdx[cc]; m.dlt = W.pdlt[cc]; m.x1 = W.px1[cc];
+                m.dkk = 0.0; m.pv = 0.0;
+#pragma unroll
+                for (int r = 0; r < NRA; ++r) m.dtv[r] = 0.0;
+                if (fast && m.cd.sec >= 0) {
+                    const OgbSec& S = P.sec[m.cd.sec];
+                    if (m.cd.blk < S.ns) {
+                        const double* __restrict__ Dt = P.Dt + S.doff + m.cd.k * S.N;
+#pragma unroll
+                        for (int r = 0; r < NRA; ++r) {
+                            const int i = lane + 32 * r;
+                            if (i < S.N) m.dtv[r] = __ldg(Dt + i);
+                        }
+                        m.dkk = __ldg(Dt + m.cd.k);
+                    }
+                    if (lane < S.nouts) m.pv = W.pert[lane * W.G + cc];
+                }
+            };
+            ColMeta nxt;
+            if (warp < ncols) load_meta(warp, nxt);
             for (int cc = warp; cc < ncols; cc += nwarps) {
+                const ColMeta cur = nxt;
+                if (cc + nwarps < ncols) load_meta(cc + nwarps, nxt);
                 const int j = jlo + cc;
                 double* __restrict__ gdst = Jb + (unsigned)j * (unsigned)M;
-                const OgbCol cd = W.pcol[cc];
-                const double dx = W.pdx[cc], rdx = W.prdx[cc];
+                const OgbCol cd = cur.cd;
+                const double dx = cur.dx, rdx = cur.rdx;
                 const bool fcol = fast && cd.sec >= 0;
                 const int a = (fcol && cd.blk < P.sec[cd.sec].ns) ? cd.blk : -1;
-                // issue the D^T row loads first so their latency hides behind the zero stream
-                double dtv[NRA], dkk = 0.0;
-                if (a >= 0) {
-                    const OgbSec& S = P.sec[cd.sec];
-                    const double* __restrict__ Dt = P.Dt + S.doff + cd.k * S.N;
-#pragma unroll
-                    for (int r = 0; r < NRA; ++r) {
-                        const int i = lane + 32 * r;
-                        dtv[r] = i < S.N ? __ldg(Dt + i) : 0.0;
-                    }
-                    dkk = __ldg(Dt + cd.k);
-                }
                 {   // zeros: 16-byte aligned body, an odd first / last double on its own
                     const unsigned hj = (unsigned)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
                     const unsigned nbytes = ((unsigned)(M - hj) & ~1u) * 8u;
@@ -301,7 +316,11 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 if (fcol) {
                     const OgbSec& S = P.sec[cd.sec];
                     const int N = S.N, k = cd.k;
-                    const double dlt = W.pdlt[cc];
+                    const double dlt = cur.dlt;
+                    if (cd.sec != slot_sec) {                    // new phase: this lane's slot record
+                        slot_sec = cd.sec;
+                        si = lane < S.nouts ? slots[S.out_off + lane] : OgbSlot{0, 0, 0, 0};
+                    }
                     if (a >= 0) {
                         if (cd.sec != cur_sec || cd.blk != cur_blk) {    // new state block: reload row constants
                             cur_sec = cd.sec; cur_blk = cd.blk;
@@ -320,26 +339,36 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                         for (int r = 0; r < NRA; ++r) {
                             const int i = lane + 32 * r;
                             if (i < N && i != k) {
-                                const double cp = (r_sdx[r] + dtv[r] * dlt) - r_cf[r];
+                                const double cp = (r_sdx[r] + cur.dtv[r] * dlt) - r_cf[r];
                                 crow[i] = ogb_fd_div(cp - r_sc[r], dx, rdx);
                             }
                         }
                     }
                     const double coef = W.coef[3 * cd.sec];
-                    for (int t = lane; t < S.nouts; t += 32) {
-                        const OgbSlot si = slots[S.out_off + t];
-                        if (k >= si.klo && k < si.khi) {
+                    if (k >= si.klo && k < si.khi) {             // slot t = lane (slots 0..31)
+                        double cp = cur.pv;
+                        const int r = si.rbase + k;
+                        if (si.isdyn) {
+                            double dxp = W.sdx[S.dxoff + lane * N + k];
+                            if (lane == a) dxp = dxp + cur.dkk * dlt;
+                            cp = dxp - coef * cp;
+                        }
+                        gdst[r] = ogb_fd_div(cp - W.sc[r], dx, rdx);
+                    }
+                    for (int t = lane + 32; t < S.nouts; t += 32) {   // (rare) more than 32 output slots
+                        const OgbSlot s2 = slots[S.out_off + t];
+                        if (k >= s2.klo && k < s2.khi) {
                             double cp = W.pert[t * W.G + cc];
-                            const int r = si.rbase + k;
-                            if (si.isdyn) {
+                            const int r = s2.rbase + k;
+                            if (s2.isdyn) {
                                 double dxp = W.sdx[S.dxoff + t * N + k];
-                                if (t == a) dxp = dxp + dkk * dlt;
+                                if (t == a) dxp = dxp + cur.dkk * dlt;
                                 cp = dxp - coef * cp;
                             }
                             gdst[r] = ogb_fd_div(cp - W.sc[r], dx, rdx);
                         }
                     }
-                    if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots(P, W, j, W.px1[cc], dx, rdx, col, lane, 32);
+                    if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots(P, W, j, cur.x1, dx, rdx, col, lane, 32);
                     ogb_scatter_scalar_cost(P, W, cd, cc, dx, rdx, col, lane, 32);
                 } else {
                     ogb_scatter_column(P, W, j, cc, col, lane, 32);

@@ -46,3 +46,11 @@ for _ in range(K):
 e1.record()
 torch.cuda.synchronize()
 print("eval   : %.4f ms" % (e0.elapsed_time(e1) / K))
+# write-only bandwidth of this GPU for reference (memset of J)
+e0.record()
+for _ in range(K):
+    J.zero_()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / K
+print("memset of J: %.3f ms  %.1f GB/s" % (ms, J.numel() * 8 / ms / 1e6))
