@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256, OGB_MIN_BLOCKS)
 ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const double* __restrict__ DX,
                  const double* __restrict__ lb, const double* __restrict__ ub, double abs_step,
                  int B, double* __restrict__ c, double* __restrict__ J, int with_fd,
-                 int ncode, int nconsts, int nouts, int force_generic) {
+                 int ncode, int nconsts, int nouts, int force_generic, unsigned long long* ticket) {
     extern __shared__ __align__(16) double smem[];
 #ifdef OGB_SPEC_M                     // NVRTC build: the problem's sizes are compile-time constants
     P.M = OGB_SPEC_M; P.n = OGB_SPEC_NVARS; P.meq = OGB_SPEC_MEQ; P.mineq = OGB_SPEC_MINEQ;
@@ -101,6 +101,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     W.G = pl.G;
     OgbSlot* slots = reinterpret_cast<OgbSlot*>(smem + pl.o_slot);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + pl.o_end);     // [2]
+    volatile long* s_next = reinterpret_cast<volatile long*>(smem + pl.o_end + 2);   // next work item
 
     // ---- once per CTA: problem descriptors and tapes into shared memory
     {
@@ -160,19 +161,25 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
 
     const int meq = P.meq;
 
+    // Work items are claimed dynamically (one atomic ticket per item; the first item of a CTA is
+    // its index) so all CTAs finish within one item of each other.  The ticket for item i+1 is
+    // requested at the top of item i and read after the tape phase (its latency is off the critical
+    // path); the inputs of item i+1 are then prefetched while item i assembles and streams out.
     if ((long)blockIdx.x < nitems) stage_inputs(blockIdx.x, 0);
     __syncthreads();                 // the odd head / tail doubles of the first item are in place
     unsigned it = 0;
-    for (long item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+    for (long item = blockIdx.x; item < nitems; ++it) {
         const long b = item / nchunk;
         const int ch = (int)(item - b * nchunk);
         const int jlo = with_fd ? ch * pl.G : 0;
         const int ncols = with_fd ? min(pl.G, n - jlo) : 0;
         const int st = (int)(it & 1u);
+        long claimed = 0;
+        if (tid == 0)
+            claimed = ticket ? (long)gridDim.x + (long)atomicAdd(ticket, 1ULL) : item + (long)gridDim.x;
 
-        // ---- phase 1: prefetch the next item's inputs, then take this item's (issued one
-        //      item ago, so the TMA engine served them ahead of the Jacobian stores)
-        if (item + gridDim.x < nitems) stage_inputs(item + gridDim.x, st ^ 1);
+        // ---- phase 1: take this item's inputs (their TMA loads were issued one item ago, so the
+        //      copy engine served them long before they are needed)
         {
             const double* gp = p + b * n;
             const double* gdx = fused_dx ? nullptr : DX + b * ndx;
@@ -228,7 +235,10 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
 
         // ---- phase 2: tapes -- base nodes, scalar program, one job per Jacobian column
         for (int q = tid; q < P.gtot + 1 + ncols; q += nthr) ogb_job(P, W, q, jlo, lb, ub, abs_step);
+        if (tid == 0) *s_next = claimed;
         __syncthreads();
+        const long next_item = *s_next;
+        if (next_item < nitems) stage_inputs(next_item, st ^ 1);      // prefetch one item ahead
 
         // ---- phase 3: c at the base point and the perturbed cost of every column.  Without a
         //      running cost neither depends on the other, so one barrier covers both.
@@ -376,6 +386,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             }
         }
         __syncthreads();             // all warps are done reading this item's staging
+        item = next_item;
     }
 }
 
