@@ -158,6 +158,8 @@ enum ogb_option {
     OGB_OPT_GRID_CAP = 3,        /* cap on the persistent grid (0 = SM count x resident CTAs)         */
     OGB_OPT_DYNAMIC_ITEMS = 5,   /* 1 (default): persistent CTAs claim work items with an atomic ticket;
                                     0: static round-robin assignment                                    */
+    OGB_OPT_GROUP_COLS = 6,      /* cap on Jacobian columns per work item (default 256); an instance is
+                                    split into ceil(nvars / cap) items                                 */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
                                     launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
                                     (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */

@@ -88,9 +88,9 @@ static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, si
 }
 
 static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts, size_t nouts,
-                                 OgbPlan* pl, std::string* err, int force_warps = 0) {
+                                 OgbPlan* pl, std::string* err, int force_warps = 0, int gmax = 0) {
     const size_t SMEM_MAX = 227 * 1024, SM_SMEM = 228 * 1024;
-    const int GMAX = 224;
+    const int GMAX = gmax > 0 ? gmax : 256;          // Jacobian columns staged per work item (measured: tools/sweep_group.py)
     pl->split = (P.n + GMAX - 1) / GMAX;
     pl->G = (P.n + pl->split - 1) / pl->split;
     // pick the CTA size (2..8 warps) that keeps the most warps resident per SM; registers
