@@ -46,6 +46,9 @@ struct OgbSec {
     int run_slot;           // output slot carrying the running-cost integrand, -1 = none
     int pad;
 };
+#ifdef OGB_SPEC_SECTIONS               // NVRTC build: the records are a constant table (see ogb_sec)
+extern __device__ const OgbSec ogb_spec_sec[];
+#endif
 
 struct OgbKnot {            // one smooth-state knot row (optimize.py:689-696)
     int row, var_prev, var_post, pad;
@@ -114,6 +117,14 @@ struct OgbPlan {
         o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_prdx, o_slot, o_tiles, tile_stride, o_tail,
         tail_stride, o_end;
 };
+
+// Phase record s.  In the NVRTC build the records are compile-time constants
+// (ogb_spec_sec, emitted by ogb_jit.h), so every field folds into an immediate.
+#ifdef OGB_SPEC_SECTIONS
+OGB_HD const OgbSec& ogb_sec(const OgbProb&, int s) { return ogb_spec_sec[OGB_SPEC_NSEC == 1 ? 0 : s]; }
+#else
+OGB_HD const OgbSec& ogb_sec(const OgbProb& P, int s) { return P.sec[s]; }
+#endif
 
 // ------------------------------------------------------------------ LGL basis
 // P_n and P_n' by the three-term recurrence.
@@ -319,7 +330,7 @@ OGB_HD double ogb_fd_div(double a, double dx, double rdx) {
 
 OGB_HD int ogb_sec_of_node(const OgbProb& P, int g) {
     int s = 0;
-    while (s + 1 < P.nsec && g >= P.sec[s + 1].g0) ++s;
+    while (s + 1 < P.nsec && g >= ogb_sec(P, s + 1).g0) ++s;
     return s;
 }
 
@@ -365,14 +376,14 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
                     const double* lb, const double* ub, double abs_step) {
     if (q < P.gtot) {
         const int s = ogb_sec_of_node(P, q);
-        const OgbSec& S = P.sec[s];
+        const OgbSec& S = ogb_sec(P, s);
         OgbNodeLoad ld{W.sp + S.off + (q - S.g0), S.N, -1, 0.0};
         OGB_NODE_PROGRAM(s, S, ld, W.sbase + q, P.gtot);
     } else if (q == P.gtot) {
         OgbScalarLoad ld{W.sp, -1, 0.0};
         OGB_SCALAR_PROGRAM(ld, W.scbase, 1);
         for (int s = 0; s < P.nsec; ++s) {
-            const OgbSec& S = P.sec[s];
+            const OgbSec& S = ogb_sec(P, s);
             const double tfx = ogb_nd(W.sp[S.tf_idx], P.unit_time);                 // :684
             const double tix = S.t0_idx < 0 ? P.t0x : ogb_nd(W.sp[S.t0_idx], P.unit_time);  // :683
             W.coef[3 * s + 0] = (tfx - tix) / 2.0;                                  // :686
@@ -392,7 +403,7 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
         W.pcol[cl] = col;
         double dlt = 0.0;
         if (col.sec >= 0) {
-            const OgbSec& S = P.sec[col.sec];
+            const OgbSec& S = ogb_sec(P, col.sec);
             if (col.blk < S.ns) {
                 const double u = P.ustate[S.us_off + col.blk];
                 dlt = ogb_nd(x1, u) - ogb_nd(x0, u);
@@ -412,7 +423,7 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
 OGB_HD void ogb_assemble_base(const OgbProb& P, const OgbWork& W, int tid, int nthr) {
     // collocation defects  D.x - (tf - t0)/2 * f   (optimize.py:686)
     for (int s = 0; s < P.nsec; ++s) {
-        const OgbSec& S = P.sec[s];
+        const OgbSec& S = ogb_sec(P, s);
         const double coef = W.coef[3 * s];
         for (int e = tid; e < S.ns * S.N; e += nthr) {
             const int a = e / S.N, i = e - a * S.N;
@@ -476,7 +487,7 @@ OGB_HD void ogb_cost_column(const OgbProb& P, const OgbWork& W, int cl) {
     if (P.has_running) {
         double acc = W.prefix[P.gtot];
         if (cd.sec >= 0) {
-            const OgbSec& S = P.sec[cd.sec];
+            const OgbSec& S = ogb_sec(P, cd.sec);
             const int g = S.g0 + cd.k;
             acc = W.prefix[g] + W.pert[S.run_slot * W.G + cl] * P.w[g];
             for (int g2 = g + 1; g2 < P.gtot; ++g2) acc += W.rterm[g2];
@@ -516,9 +527,9 @@ OGB_HD void ogb_scatter_drows(const OgbProb& P, const OgbWork& W, const OgbSec& 
 }
 
 // rows living at node k: every state's defect row (dynamics moved) and the pointwise user rows
-OGB_HD void ogb_scatter_noderows(const OgbProb& P, const OgbWork& W, const OgbSec& S, int a, int k,
+OGB_HD void ogb_scatter_noderows(const OgbProb& P, const OgbWork& W, const OgbSec& S, int sidx, int a, int k,
                                  int cl, double dlt, double dx, double rdx, const OgbColOut& col, int lane, int nlanes) {
-    const double coef = W.coef[3 * (int)(&S - P.sec)];
+    const double coef = W.coef[3 * sidx];
     const int g = S.g0 + k;
     for (int slot = lane; slot < S.nouts; slot += nlanes) {
         if (slot < S.ns) {
@@ -555,7 +566,7 @@ OGB_HD void ogb_scatter_time(const OgbProb& P, const OgbWork& W, int j, int sec,
                              double rdx, const OgbColOut& col, int lane, int nlanes) {
     const double tfx1 = ogb_nd(x1, P.unit_time);
     for (int s = sec; s < P.nsec && s <= sec + 1; ++s) {
-        const OgbSec& S = P.sec[s];
+        const OgbSec& S = ogb_sec(P, s);
         double coef1;
         if (s == sec) coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0;
         else if (S.t0_idx == j) coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0;
@@ -587,11 +598,11 @@ OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl
     const double dx = W.pdx[cl], rdx = W.prdx[cl];
     const double x1 = W.px1[cl];
     if (cd.sec >= 0) {
-        const OgbSec& S = P.sec[cd.sec];
+        const OgbSec& S = ogb_sec(P, cd.sec);
         const double dlt = W.pdlt[cl];
         const int a = cd.blk < S.ns ? cd.blk : -1;
         if (a >= 0) ogb_scatter_drows(P, W, S, a, cd.k, dlt, dx, rdx, col, lane, nlanes);
-        ogb_scatter_noderows(P, W, S, a, cd.k, cl, dlt, dx, rdx, col, lane, nlanes);
+        ogb_scatter_noderows(P, W, S, cd.sec, a, cd.k, cl, dlt, dx, rdx, col, lane, nlanes);
         if (P.nknot) ogb_scatter_knots(P, W, j, x1, dx, rdx, col, lane, nlanes);
     } else {
         ogb_scatter_time(P, W, j, cd.blk, x1, dx, rdx, col, lane, nlanes);

@@ -116,7 +116,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     __syncthreads();
     const bool fast = NR > 0 && !force_generic;
     for (int s = 0; s < P.nsec; ++s) {
-        const OgbSec& S = P.sec[s];
+        const OgbSec& S = ogb_sec(P, s);
         for (int t = tid; t < S.nouts; t += nthr) {
             const ogb_out o = P.outs[S.out_off + t];
             OgbSlot si = {0, 0, 0, 0};
@@ -204,7 +204,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             const int qr = lane >> 2, qc = lane & 3;
             int unit0 = 0;
             for (int s = 0; s < P.nsec; ++s) {
-                const OgbSec& S = P.sec[s];
+                const OgbSec& S = ogb_sec(P, s);
                 const int N = S.N, Kp = (N + 3) & ~3;
                 const int mt = (S.ns + 7) >> 3, nt = (N + 7) >> 3;
                 const double* __restrict__ Dm = P.D + S.doff;
@@ -277,7 +277,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
 #pragma unroll
                 for (int r = 0; r < NRA; ++r) m.dtv[r] = 0.0;
                 if (fast && m.cd.sec >= 0) {
-                    const OgbSec& S = P.sec[m.cd.sec];
+                    const OgbSec& S = ogb_sec(P, m.cd.sec);
                     if (m.cd.blk < S.ns) {
                         const double* __restrict__ Dt = P.Dt + S.doff + m.cd.k * S.N;
 #pragma unroll
@@ -300,7 +300,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 const OgbCol cd = cur.cd;
                 const double dx = cur.dx, rdx = cur.rdx;
                 const bool fcol = fast && cd.sec >= 0;
-                const int a = (fcol && cd.blk < P.sec[cd.sec].ns) ? cd.blk : -1;
+                const int a = (fcol && cd.blk < ogb_sec(P, cd.sec).ns) ? cd.blk : -1;
                 {   // zeros: 16-byte aligned body, an odd first / last double on its own
                     const unsigned hj = (unsigned)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
                     const unsigned nbytes = ((unsigned)(M - hj) & ~1u) * 8u;
@@ -324,7 +324,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 __syncwarp();
                 const OgbColOut col{gdst, gdst + meq, meq};
                 if (fcol) {
-                    const OgbSec& S = P.sec[cd.sec];
+                    const OgbSec& S = ogb_sec(P, cd.sec);
                     const int N = S.N, k = cd.k;
                     const double dlt = cur.dlt;
                     if (cd.sec != slot_sec) {                    // new phase: this lane's slot record
