@@ -107,7 +107,8 @@ struct OgbWork {            // per work item scratch (shared memory on the devic
 struct OgbPlan {
     int threads;        // CTA size of the sweep kernel (every warp produces Jacobian columns)
     int G;              // Jacobian columns per work item (perturbed-output staging capacity)
-    int split;          // work items per instance = ceil(n / G)
+    int split;          // work items per instance = ceil(n / group); chosen per launch
+    int group;          // Jacobian columns per work item (<= G)
     int TC;             // warps per CTA
     int nbuf;           // dense column buffers per warp
     unsigned long long smem_bytes;  // dynamic shared memory

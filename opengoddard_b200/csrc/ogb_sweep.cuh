@@ -87,7 +87,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     P.gtot = OGB_SPEC_GTOT; P.ndx = OGB_SPEC_NDX; P.nsec = OGB_SPEC_NSEC; P.nknot = OGB_SPEC_NKNOT;
     P.npick = OGB_SPEC_NPICK; P.has_running = OGB_SPEC_RUNNING; P.sc_nouts = OGB_SPEC_SC_NOUTS;
     P.sc_cost_slot = OGB_SPEC_SC_COST_SLOT; P.max_nouts = OGB_SPEC_MAX_NOUTS;
-    pl.G = OGB_SPEC_G; pl.split = OGB_SPEC_SPLIT;
+    pl.G = OGB_SPEC_G;
 #endif
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -171,8 +171,8 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     for (long item = blockIdx.x; item < nitems; ++it) {
         const long b = item / nchunk;
         const int ch = (int)(item - b * nchunk);
-        const int jlo = with_fd ? ch * pl.G : 0;
-        const int ncols = with_fd ? min(pl.G, n - jlo) : 0;
+        const int jlo = with_fd ? ch * pl.group : 0;
+        const int ncols = with_fd ? min(pl.group, n - jlo) : 0;
         const int st = (int)(it & 1u);
         long claimed = 0;
         if (tid == 0)

@@ -82,8 +82,8 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
         emu_dx_gemm(h, pclip.data(), 1, dxs.data());
         const int nchunk = with_fd ? pl.split : 1;
         for (int ch = 0; ch < nchunk; ++ch) {
-            const int jlo = with_fd ? ch * pl.G : 0;
-            const int ncols = with_fd ? std::min(pl.G, P.n - jlo) : 0;
+            const int jlo = with_fd ? ch * pl.group : 0;
+            const int ncols = with_fd ? std::min(pl.group, P.n - jlo) : 0;
             for (int j = 0; j < P.n; ++j) W.sp[j] = pclip[j];
             for (int e = 0; e < P.ndx; ++e) W.sdx[e] = dxs[e];
             for (int q = 0; q < P.gtot + 1 + ncols; ++q) ogb_job(P, W, q, jlo, lb, ub, abs_step);

@@ -37,6 +37,7 @@ timeit("default (jit=%d)" % eng.info.jit)
 eng.set_option(2, 0); timeit("interpreter kernel"); eng.set_option(2, 1)
 eng.set_option(4, 1); timeit("D.X fused into K2"); eng.set_option(4, 0)
 eng.set_option(5, 0); timeit("static item assignment"); eng.set_option(5, 1)
+eng.set_option(7, 0); timeit("no auto split"); eng.set_option(7, 1)
 eng.set_option(0, 1); timeit("generic columns"); eng.set_option(0, 0)
 for thr in (64, 128, 192, 256):
     try:
