@@ -159,6 +159,9 @@ class DeviceProblem:
         self.launches += 1 if self.fused_dx else 2
         return c, J
 
+    def host_evaluator(self):
+        return _HostEvaluator(self)
+
     # ------------------------------------------------------------------ single-instance host API
     # (what Problem.solve hands to SciPy: host vector in, host arrays out, pinned staging)
     def _staging(self):
@@ -191,6 +194,23 @@ class DeviceProblem:
         s["hJ"].copy_(s["dJ"], non_blocking=True)
         self.torch.cuda.current_stream(self.device).synchronize()
         return s["hc"].numpy()[0].copy(), s["hJ"].numpy()[0].copy()
+
+
+class _HostEvaluator:
+    """numpy in / numpy out view of a DeviceProblem for sqp.slsqp_batch."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def eval(self, X):
+        t = self.eng.torch
+        c = self.eng.eval(t.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.eng.device))
+        return c.cpu().numpy()
+
+    def eval_fd(self, X):
+        t = self.eng.torch
+        c, J = self.eng.eval_fd(t.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.eng.device))
+        return c.cpu().numpy(), J.cpu().numpy()
 
 
 def lgl_device(N, device="cuda:0"):

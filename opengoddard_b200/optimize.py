@@ -326,6 +326,42 @@ class Problem:
         eng = self._engine if self._engine is not None else self.compile(obj)
         return eng.eval_fd(P) if jacobian else eng.eval(P)
 
+    def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1):
+        """Multi-start: solve the NLP from every row of P0 (B, nvars) at once.
+
+        Every instance runs SciPy's SLSQP state machine (same C core as `solve`); all function
+        and Jacobian evaluations of an SQP step are served by one batched device call
+        (sqp.slsqp_batch).  Like `solve` (reference optimize.py:738-755) instances that did not
+        reach exit mode 0 are restarted from where they stopped, up to `max_outer`
+        (default maxIterator) times.  Returns dict(x, fun, status, nit, outer)."""
+        from . import sqp
+        self._check_callbacks()
+        eng = self._engine if self._engine is not None else self.compile(obj)
+        lb, ub = self.bounds_arrays()
+        X = np.array(np.atleast_2d(P0), dtype=np.float64)
+        B = X.shape[0]
+        status = np.full(B, 9)
+        fun = np.zeros(B)
+        nit = np.zeros(B, dtype=int)
+        outer = np.zeros(B, dtype=int)
+        grad = None
+        if self.cost_derivative is not None:
+            def grad(x):
+                self.p = x
+                return np.ascontiguousarray(self.cost_derivative(self, obj), dtype=np.float64)
+        for _ in range(self.maxIterator if max_outer is None else max_outer):
+            ids = np.nonzero(status != 0)[0]
+            if ids.size == 0:
+                break
+            res = sqp.slsqp_batch(eng.host_evaluator(), X[ids], lb, ub, eng.meq, eng.mineq, ftol=ftol,
+                                  maxiter=maxiter, cost_grad=grad, threads=threads)
+            X[ids] = res["x"]
+            status[ids] = res["status"]
+            fun[ids] = res["fun"]
+            nit[ids] += res["nit"]
+            outer[ids] += 1
+        return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
+
     # ------------------------------------------------------------------ solve (:649-755)
     def _dummy_func():
         pass
@@ -381,7 +417,9 @@ class Problem:
                 {"type": "ineq", "fun": lambda x, *a: c_at(x)[meq:meq + mineq],
                  "jac": lambda x, *a: j_at(x)[:, meq:meq + mineq].T, "args": (self, obj)})
         if self.cost_derivative is None:
-            jac = lambda x, *a: j_at(x)[:, M - 1]
+            # contiguous copy: SciPy 1.18's low-level SLSQP step reads a strided gradient as if it
+            # were contiguous (checked in tests/test_sqp.py), and J[:, M-1] is a strided column
+            jac = lambda x, *a: np.ascontiguousarray(j_at(x)[:, M - 1])
         else:
             def jac(x, *a):                               # user gradient, host (reference :733)
                 self.p = x

@@ -190,3 +190,18 @@ def test_solve_goddard_device_vs_host_backend(torch_cuda, api, monkeypatch, caps
         assert alt[backend] > 1.005                      # started from h(t_f) = 1.010 infeasible guess
     capsys.readouterr()
     assert abs(alt["cuda"] - alt["host"]) < 5e-3
+
+
+def test_solve_batch_multistart(torch_cuda, api, capsys):
+    """Batched SQP driver on the device: every start converges to the brachistochrone optimum, and
+    instance 0 (the shipped guess) follows exactly the trajectory of the single-instance `solve`."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    P0 = np.vstack([np.array(wl.prob.p)[None], workloads.make_batch(wl, 5)])
+    res = wl.prob.solve_batch(P0, wl.obj, ftol=1e-6, maxiter=25)
+    assert (res["status"] == 0).all()
+    assert np.abs(res["x"][:, -1] - np.sqrt(np.pi)).max() < 2e-4
+    single = workloads.build("cfg1_brachistochrone20", api)
+    single.prob.solve(single.obj)
+    capsys.readouterr()
+    assert np.array_equal(np.asarray(single.prob.p), res["x"][0])

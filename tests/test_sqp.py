@@ -1,0 +1,111 @@
+"""Batched SQP driver (opengoddard_b200/sqp.py): host logic against SciPy itself, with the oracle
+standing in for the device evaluator (the GPU variant is in test_gpu_parity.py)."""
+import numpy as np
+import pytest
+from scipy import optimize
+
+from opengoddard_b200 import sqp, workloads
+from oracle import og_numpy
+
+
+class OracleEvaluator:
+    def __init__(self, wl):
+        self.wl = wl
+        self.lb, self.ub = og_numpy.bounds_arrays(wl.prob)
+        self.calls = []
+
+    def eval(self, X):
+        self.calls.append(("f", len(X)))
+        return np.stack([og_numpy.eval_c(self.wl.prob, self.wl.obj, x) for x in X])
+
+    def eval_fd(self, X):
+        self.calls.append(("g", len(X)))
+        cs, Js = [], []
+        for x in X:
+            c, J = og_numpy.eval_fd(self.wl.prob, self.wl.obj, x, self.lb, self.ub)
+            cs.append(c)
+            Js.append(np.ascontiguousarray(J.T))
+        return np.stack(cs), np.stack(Js)
+
+
+def scipy_reference(wl, ev, x0, meq, mineq, ftol, maxiter):
+    """scipy.optimize.minimize on the same callables (contiguous gradients)."""
+    M = meq + mineq
+    c_at = lambda x: og_numpy.eval_c(wl.prob, wl.obj, x)
+    j_at = lambda x: og_numpy.eval_fd(wl.prob, wl.obj, x, ev.lb, ev.ub)[1]
+    cons = ({"type": "eq", "fun": lambda x: c_at(x)[:meq], "jac": lambda x: j_at(x)[:meq]},
+            {"type": "ineq", "fun": lambda x: c_at(x)[meq:M], "jac": lambda x: j_at(x)[meq:M]})
+    return optimize.minimize(lambda x: c_at(x)[M], x0, jac=lambda x: np.ascontiguousarray(j_at(x)[M]),
+                             bounds=wl.prob.bounds, constraints=cons, method="SLSQP",
+                             options={"maxiter": maxiter, "ftol": ftol})
+
+
+def test_batch_of_one_reproduces_scipy_minimize():
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    ev = OracleEvaluator(wl)
+    meq, mineq = 64, 41
+    x0 = wl.prob.p.copy()
+    res = sqp.slsqp_batch(ev, x0[None], ev.lb, ev.ub, meq, mineq, ftol=1e-6, maxiter=12)
+    ref = scipy_reference(wl, ev, x0, meq, mineq, 1e-6, 12)
+    assert res["status"][0] == ref.status and res["nit"][0] == ref.nit
+    assert np.array_equal(res["x"][0], ref.x)
+    assert res["fun"][0] == ref.fun
+
+
+def test_instances_are_independent_and_batched():
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    ev = OracleEvaluator(wl)
+    meq, mineq = 64, 41
+    P = np.vstack([wl.prob.p[None], workloads.make_batch(wl, 2)])
+    res = sqp.slsqp_batch(ev, P, ev.lb, ev.ub, meq, mineq, ftol=1e-6, maxiter=6)
+    assert ev.calls[0] == ("g", 3)                          # one batched call serves all instances
+    assert max(k for _, k in ev.calls) == 3
+    for b in range(3):
+        one = sqp.slsqp_batch(OracleEvaluator(wl), P[b][None], ev.lb, ev.ub, meq, mineq, ftol=1e-6, maxiter=6)
+        assert np.array_equal(one["x"][0], res["x"][b]) and one["status"][0] == res["status"][b]
+    two = sqp.slsqp_batch(OracleEvaluator(wl), P, ev.lb, ev.ub, meq, mineq, ftol=1e-6, maxiter=6, threads=2)
+    assert np.array_equal(two["x"], res["x"])
+
+
+def test_converges_like_the_reference_outer_loop():
+    """Restarting unfinished instances (reference optimize.py:738-755) reaches t_f = sqrt(pi)."""
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    ev = OracleEvaluator(wl)
+    meq, mineq = 64, 41
+    X = wl.prob.p[None].copy()
+    grad = lambda x: wl.prob.eval_cost_derivative(x, wl.obj)
+    for _ in range(6):
+        res = sqp.slsqp_batch(ev, X, ev.lb, ev.ub, meq, mineq, ftol=1e-6, maxiter=25, cost_grad=grad)
+        X = res["x"]
+        if res["status"][0] == 0:
+            break
+    assert res["status"][0] == 0
+    assert abs(X[0, -1] - 1.7724608832526498) < 1e-4
+
+
+def test_scipy_slsqp_needs_contiguous_gradient():
+    """Documented SciPy 1.18 behaviour the facade guards against: the low-level step reads a
+    strided gradient array as if it were contiguous."""
+    slsqp, _ = sqp._low_level()
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    lb, ub = og_numpy.bounds_arrays(wl.prob)
+    n, meq, m = 81, 64, 105
+    x0 = np.clip(wl.prob.p, lb, ub)
+    c, J = og_numpy.eval_fd(wl.prob, wl.obj, x0, lb, ub)
+
+    def one_step(g):
+        it = sqp._Instance(x0, n, m, meq, 1e-6, 2, np.int32)
+        it.C[:m] = J[:m]
+        it.d[:m] = c[:m]
+        xl = np.where(np.isfinite(lb), lb, np.nan)
+        xu = np.where(np.isfinite(ub), ub, np.nan)
+        slsqp(it.state, float(c[m]), g, it.C, it.d, it.x, it.mult, xl, xu, it.buffer, it.indices)
+        return it.x
+
+    g = np.ascontiguousarray(J[m])
+    strided = np.ascontiguousarray(J.T)[:, m]
+    assert np.array_equal(g, strided) and not strided.flags["C_CONTIGUOUS"]
+    good, bad = one_step(g), one_step(strided)
+    if np.array_equal(good, bad):
+        pytest.skip("this SciPy handles strided gradients")
+    assert not np.array_equal(good, bad)
