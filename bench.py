@@ -17,8 +17,9 @@ collective; rank 0 prints ONE JSON line.
 Timing: W >= 3 warm-up steps, then exactly K timed steps, each bracketed by CUDA events
 on the launching stream; a 256 MiB memset flushes L2 between steps outside the event
 pairs (each step also writes ~3 GB, 24x L2).  Time = sum of the K event durations, MAX
-over ranks.  `e2e` repeats the measurement through the host-buffer API: pinned host p
--> H2D -> kernels -> D2H of c and J into pinned host memory, all inside the timed region.
+over ranks.  `e2e` repeats the measurement through the host-buffer C-ABI call
+(ogb_host_eval_fd): pinned host p -> H2D -> K1 -> K2 -> K3 pack -> D2H of c and the packed non-zeros
+-> host threads write the dense J into host memory, all inside the timed region (host clock).
 """
 import argparse
 import json
@@ -222,6 +223,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: per workload)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-variants", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads of the e2e session (default: cores / ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg, default_batch = WORKLOADS[args.workload]
@@ -320,29 +323,57 @@ def main():
     total_ms = float(total_ms.item())
     value = world * B * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the host-buffer API (pinned host in, pinned host out)
+    # ---- end to end through the host-buffer C-ABI entry point (ogb_host_eval_fd): p in pinned HOST
+    #      memory in, c and the dense J in HOST memory out, every copy inside the timed region.
+    #      The call is synchronous and its last stage runs on host threads, so the clock is the
+    #      host's (perf_counter between barriers), MAX over ranks.
+    del J, flush
+    torch.cuda.empty_cache()
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 8))
-    hc = torch.empty((B, M), dtype=torch.float64).pin_memory()
-    hJ = torch.empty((B, n, M), dtype=torch.float64).pin_memory()
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    threads = args.host_threads or max(1, host_procs() // max(1, local_world))
+    sess = eng.host_session(B, threads=threads)
+    hc = np.empty((B, M), dtype=np.float64)
+    hJ = np.empty((B, n, M), dtype=np.float64)
 
-    def e2e_step():
-        P.copy_(P_host, non_blocking=True)
-        eng.eval_fd(P, out_c=c, out_J=J)
-        hc.copy_(c, non_blocking=True)
-        hJ.copy_(J, non_blocking=True)
+    def time_mode(mode, Jbuf, steps):
+        sess.eval_fd(P_host, hc, Jbuf, mode=mode)           # warm-up (also faults the pages in)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sess.eval_fd(P_host, hc, Jbuf, mode=mode)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        barrier()
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        st = sess.stats()
+        return world * B * steps / float(dt.item()), st
 
-    e2e_step()
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    t1.record()
-    barrier()
-    e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    e2e_value, st = time_mode("dense", hJ, e2e_steps)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st.h2d_bytes),
+           "d2h_bytes_per_step": int(st.d2h_bytes), "steps": e2e_steps,
+           "api": "ogb_host_eval_fd(mode=OGB_HOST_J_DENSE): pinned host p -> H2D -> K1 -> K2 -> K3 pack -> D2H of c "
+                  "and the packed non-zeros -> %d host threads rewrite the whole dense J (zeros included) in "
+                  "pageable host memory; %d chunks of %d instances; host wall clock" % (st.threads, st.nchunks, st.chunk),
+           "nnz_per_instance": int(st.nnz), "host_threads": int(st.threads)}
+    if not args.no_e2e_variants:
+        # the same call with the other transports, for context (not the headline)
+        var = {}
+        var["keep_zeros"], _ = time_mode("keep_zeros", hJ, max(2, e2e_steps // 2))
+        hv = np.empty((B, int(st.nnz)), dtype=np.float64)
+        var["packed"], _ = time_mode("packed", hv, max(2, e2e_steps // 2))
+        del hv
+        try:
+            hJp = torch.empty((B, n, M), dtype=torch.float64).pin_memory()
+            var["dma_dense_pinned"], st2 = time_mode("dma", hJp, 2)
+            e2e["dma_d2h_bytes_per_step"] = int(st2.d2h_bytes)
+            del hJp
+        except Exception as ex:                              # pinned allocation can fail on a small host
+            var["dma_dense_pinned"] = None
+            e2e["dma_error"] = str(ex)[:120]
+        e2e["variants"] = var
+    launches_e2e = int(st.launches)
+    sess.close()
 
     if rank == 0:
         peaks = {}
@@ -371,9 +402,8 @@ def main():
                              "also writes %.2f GB of Jacobian (L2 is 126 MB)" % (B * bytes_per_eval / 1e9),
                        "parallelism": "instance batch sharded over %d GPU(s), no data-path collective" % world},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * n * 8,
-                    "d2h_bytes_per_step": B * M * 8 + B * n * M * 8, "steps": e2e_steps},
-            "gpu_launches": launches,
+            "e2e": e2e,
+            "gpu_launches": launches, "gpu_launches_per_e2e_step": launches_e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "ogb_sweep_kernel (K2)",
                          "kernel_ms": sweep_avg_ms, "bytes_per_launch": B * bytes_per_eval,

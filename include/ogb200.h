@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OGB_VERSION 100
+#define OGB_VERSION 110
 
 /* ---- expression tapes -----------------------------------------------------
  * User callbacks (dynamics / equality / inequality / cost / running_cost; reference
@@ -204,6 +204,56 @@ int ogb_eval(void* prob, const double* p, int B, double* c, void* work, void* st
  * +-inf for "no bound".                                                           */
 int ogb_eval_fd(void* prob, const double* p, const double* lb, const double* ub,
                 double abs_step, int B, double* c, double* J, void* work, void* stream);
+
+/* ---- packed Jacobian transport ---------------------------------------------------------
+ * The FD Jacobian is structurally sparse: a perturbed state moves its own defect rows and the
+ * rows living at its node (eq J 7 758 / 31 155, ineq J 301 / 60 501
+ * non-zeros at Goddard-50).  Which entries of an instance's J [nvars, nrows] can be non-zero is a
+ * property of the problem, not of p.  ogb_jac_pattern returns their count and (if lin_h != NULL,
+ * cap >= count) their ascending linear indices j * nrows + r; ogb_pack gathers them from a dense
+ * device J [B, nvars, nrows] into vals [B, nnz] (kernel K3).  Entries outside the pattern are
+ * exactly 0.0 in every dense J the sweep kernel writes.                                        */
+int ogb_jac_pattern(void* prob, uint32_t* lin_h, int cap);
+int ogb_pack(void* prob, const double* J, int B, double* vals, void* stream);
+
+/* ---- host-buffer entry point -----------------------------------------------------------
+ * What the reference's SciPy-facing closures are to a host caller: decision vectors in HOST
+ * memory in, c and the dense FD Jacobian in HOST memory out (reference optimize.py:711-715 +
+ * scipy/optimize/_slsqp_py.py:353-367, for B instances at once).  A session owns the device
+ * scratch, two CUDA streams, pinned staging and a pool of host threads for one problem on the
+ * current device.  ogb_host_eval_fd is synchronous: when it returns, c_h [B, nrows] and J_h
+ * are complete.  The batch is cut into chunks that flow through
+ *     H2D p -> K1 -> K2 (dense J in HBM) -> K3 pack -> D2H packed values -> host threads
+ * write the dense J_h (zeros with non-temporal stores + the packed non-zeros), so PCIe carries
+ * nnz instead of nvars * nrows doubles per instance and the copies overlap the kernels.
+ * p_h / c_h / J_h may be pageable or pinned memory.                                        */
+enum ogb_host_mode {
+    OGB_HOST_J_DENSE = 0,      /* J_h [B, nvars, nrows] fully rewritten (zeros included)              */
+    OGB_HOST_J_KEEP_ZEROS = 1, /* J_h [B, nvars, nrows] already holds this problem's zero background
+                                  (e.g. from an earlier OGB_HOST_J_DENSE call into the same buffer):
+                                  only the entries of the pattern are rewritten                       */
+    OGB_HOST_J_PACKED = 2,     /* J_h [B, nnz] receives the packed values (pattern: ogb_jac_pattern)  */
+    OGB_HOST_J_DMA = 3         /* J_h [B, nvars, nrows] written by one dense device->host copy (the
+                                  transport without packing; fastest into pinned memory)              */
+};
+
+typedef struct ogb_host_stats {
+    int64_t h2d_bytes, d2h_bytes;   /* bytes copied over PCIe by the last call                        */
+    int32_t launches;               /* kernels launched by the last call                              */
+    int32_t nnz, chunk, threads, nchunks, pad;
+    double ms_total, ms_first_chunk;/* wall time of the last call; time until the first chunk landed  */
+} ogb_host_stats;
+
+void* ogb_host_session_create(void* prob, int max_batch, int chunk /*0 = default*/, int threads /*0 = all*/);
+void  ogb_host_session_destroy(void* session);
+int   ogb_host_eval_fd(void* session, const double* p_h, const double* lb_h, const double* ub_h,
+                       double abs_step, int B, double* c_h, double* J_h, int mode);
+int   ogb_host_session_stats(void* session, ogb_host_stats* out);
+
+/* The host half of the transport by itself (no GPU involved): expand packed values [B, nnz] into
+ * dense J_h [B, nM] (mode OGB_HOST_J_DENSE or OGB_HOST_J_KEEP_ZEROS) with `threads` threads.   */
+int ogb_host_expand(const double* vals_h, const uint32_t* lin_h, int nnz, size_t nM, int B,
+                    double* J_h, int mode, int threads);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,15 @@ class OgbProblemInfo(C.Structure):
                                           "tile_cols", "group_cols", "smem_bytes", "ctas_per_sm", "jit")]
 
 
+class OgbHostStats(C.Structure):
+    _fields_ = [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("launches", C.c_int32),
+                ("nnz", C.c_int32), ("chunk", C.c_int32), ("threads", C.c_int32), ("nchunks", C.c_int32),
+                ("pad", C.c_int32), ("ms_total", C.c_double), ("ms_first_chunk", C.c_double)]
+
+
+HOST_MODES = {"dense": 0, "keep_zeros": 1, "packed": 2, "dma": 3}     # enum ogb_host_mode
+
+
 class OgbError(RuntimeError):
     pass
 
@@ -168,8 +177,41 @@ def ogb():
         L.ogb_eval.argtypes = [vp, dp, i32, dp, vp, vp]
         L.ogb_eval_fd.restype = C.c_int
         L.ogb_eval_fd.argtypes = [vp, dp, dp, dp, C.c_double, i32, dp, dp, vp, vp]
+        L.ogb_jac_pattern.restype = C.c_int
+        L.ogb_jac_pattern.argtypes = [vp, vp, i32]
+        L.ogb_pack.restype = C.c_int
+        L.ogb_pack.argtypes = [vp, dp, i32, dp, vp]
+        L.ogb_host_session_create.restype = C.c_void_p
+        L.ogb_host_session_create.argtypes = [vp, i32, i32, i32]
+        L.ogb_host_session_destroy.restype = None
+        L.ogb_host_session_destroy.argtypes = [vp]
+        L.ogb_host_eval_fd.restype = C.c_int
+        L.ogb_host_eval_fd.argtypes = [vp, vp, vp, vp, C.c_double, i32, vp, vp, i32]
+        L.ogb_host_session_stats.restype = C.c_int
+        L.ogb_host_session_stats.argtypes = [vp, C.POINTER(OgbHostStats)]
+        L.ogb_host_expand.restype = C.c_int
+        L.ogb_host_expand.argtypes = [vp, vp, i32, C.c_size_t, i32, vp, i32, i32]
         _ogb = b
     return _ogb
+
+
+def host_expand(vals, lin, nM, out=None, mode="dense", threads=0):
+    """ogb_host_expand: packed values (B, nnz) + ascending pattern `lin` -> dense (B, nM) host array
+    (the host half of the packed Jacobian transport; runs without a GPU)."""
+    b = ogb()
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    lin = np.ascontiguousarray(lin, dtype=np.uint32)
+    B, nnz = vals.shape
+    assert lin.shape == (nnz,)
+    if out is None:
+        assert mode == "dense"
+        out = np.empty((B, int(nM)), dtype=np.float64)
+    assert out.flags.c_contiguous and out.dtype == np.float64 and out.size == B * int(nM)
+    rc = b.lib.ogb_host_expand(vals.ctypes.data, lin.ctypes.data, nnz, int(nM), B, out.ctypes.data,
+                               HOST_MODES[mode], int(threads))
+    if rc != 0:
+        raise OgbError("ogb_host_expand failed: " + b.error())
+    return out
 
 
 def lgl_host(N):

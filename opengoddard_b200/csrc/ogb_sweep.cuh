@@ -301,7 +301,9 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 const double dx = cur.dx, rdx = cur.rdx;
                 const bool fcol = fast && cd.sec >= 0;
                 const int a = (fcol && cd.blk < ogb_sec(P, cd.sec).ns) ? cd.blk : -1;
-                {   // zeros: 16-byte aligned body, an odd first / last double on its own
+                if (with_fd != 2) {   // zeros: 16-byte aligned body, an odd first / last double on its own
+                                      // (with_fd == 2: structure probe -- only the overwrites below land,
+                                      //  on a sentinel-filled J; see ogb_jac_pattern)
                     const unsigned hj = (unsigned)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
                     const unsigned nbytes = ((unsigned)(M - hj) & ~1u) * 8u;
                     char* g = reinterpret_cast<char*>(gdst + hj) + lane * 16;

@@ -162,6 +162,33 @@ class DeviceProblem:
     def host_evaluator(self):
         return _HostEvaluator(self)
 
+    def host_session(self, max_batch, chunk=0, threads=0):
+        """Host-buffer entry point (ogb_host_eval_fd): numpy / pinned host arrays in and out."""
+        return HostSession(self, max_batch, chunk, threads)
+
+    def jac_pattern(self):
+        """Ascending linear indices j * nrows + r of the entries of one instance's J that can be
+        non-zero (ogb_jac_pattern)."""
+        with self.torch.cuda.device(self.device):
+            nnz = self.b.lib.ogb_jac_pattern(self.h, None, 0)
+            if nnz < 0:
+                self._rc(nnz, "ogb_jac_pattern")
+            lin = np.empty(nnz, dtype=np.uint32)
+            self._rc(min(0, self.b.lib.ogb_jac_pattern(self.h, lin.ctypes.data, nnz)), "ogb_jac_pattern")
+        return lin
+
+    def pack(self, J, out=None):
+        """K3: dense device J (B, nvars, nrows) -> packed (B, nnz) device tensor."""
+        t = self.torch
+        B = J.shape[0]
+        nnz = len(self.jac_pattern()) if not hasattr(self, "_nnz") else self._nnz
+        self._nnz = nnz
+        vals = out if out is not None else t.empty((B, nnz), dtype=t.float64, device=self.device)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_pack(self.h, J.data_ptr(), B, vals.data_ptr(), self._stream()), "ogb_pack")
+        self.launches += 1
+        return vals
+
     # ------------------------------------------------------------------ single-instance host API
     # (what Problem.solve hands to SciPy: host vector in, host arrays out, pinned staging)
     def _staging(self):
@@ -194,6 +221,69 @@ class DeviceProblem:
         s["hJ"].copy_(s["dJ"], non_blocking=True)
         self.torch.cuda.current_stream(self.device).synchronize()
         return s["hc"].numpy()[0].copy(), s["hJ"].numpy()[0].copy()
+
+
+class HostSession:
+    """ogb_host_session_* (include/ogb200.h): decision vectors in HOST memory in, c and J in HOST
+    memory out, B instances per call, chunked H2D -> K1 -> K2 -> K3 -> D2H (packed) -> host-thread
+    expansion.  Arrays are numpy arrays or CPU torch tensors (pinned or pageable), float64,
+    C-contiguous.  mode: "dense" (J fully rewritten), "keep_zeros" (J already holds the problem's
+    zero background), "packed" (J is (B, nnz)), "dma" (one dense device->host copy)."""
+
+    def __init__(self, eng, max_batch, chunk=0, threads=0):
+        self.eng = eng
+        self.max_batch = int(max_batch)
+        self.lb = np.ascontiguousarray(eng.lb.cpu().numpy())
+        self.ub = np.ascontiguousarray(eng.ub.cpu().numpy())
+        with eng.torch.cuda.device(eng.device):
+            self.h = eng.b.lib.ogb_host_session_create(eng.h, self.max_batch, int(chunk), int(threads))
+        if not self.h:
+            raise capi.OgbError("ogb_host_session_create failed: " + eng.b.error())
+        self.nnz = len(eng.jac_pattern())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.eng.b.lib.ogb_host_session_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ptr(a, count):
+        if isinstance(a, np.ndarray):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size >= count
+            return a.ctypes.data
+        assert a.device.type == "cpu" and a.is_contiguous() and a.numel() >= count       # torch CPU tensor
+        return a.data_ptr()
+
+    def eval_fd(self, P, c=None, J=None, mode="dense", abs_step=ABS_STEP):
+        eng = self.eng
+        if isinstance(P, np.ndarray):
+            P = np.ascontiguousarray(P, dtype=np.float64)
+        B = int(P.shape[0])
+        n, M = eng.nvars, eng.nrows
+        if c is None:
+            c = np.empty((B, M), dtype=np.float64)
+        if J is None:
+            assert mode != "keep_zeros", "keep_zeros needs the caller's prepared J"
+            J = np.empty((B, self.nnz) if mode == "packed" else (B, n, M), dtype=np.float64)
+        jcount = B * (self.nnz if mode == "packed" else n * M)
+        rc = eng.b.lib.ogb_host_eval_fd(self.h, self._ptr(P, B * n), self.lb.ctypes.data, self.ub.ctypes.data,
+                                        float(abs_step), B, self._ptr(c, B * M), self._ptr(J, jcount),
+                                        capi.HOST_MODES[mode])
+        eng._rc(rc, "ogb_host_eval_fd")
+        st = self.stats()
+        eng.launches += st.launches
+        return c, J
+
+    def stats(self):
+        st = capi.OgbHostStats()
+        self.eng._rc(self.eng.b.lib.ogb_host_session_stats(self.h, C.byref(st)), "ogb_host_session_stats")
+        return st
 
 
 class _HostEvaluator:
