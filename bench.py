@@ -244,12 +244,12 @@ def main():
         procs = host_procs()
         sample = max(256, procs * 8)
         pool = CpuPool(cfg, procs)
-        v_all, wall_all, cpu_s = pool.run(sample)
+        v_all, wall_all, cpu_s = max(pool.run(sample) for _ in range(3))     # best of 3 (noisy shared hosts)
         pool.close()
         v_one, _, _ = CpuPool(cfg, 1).run(48)
         cpu = dict(value=v_all, unit=UNIT, cores=procs, kind="port",
                    sample="%d seeded instances of %s (same generator as the GPU batch), oracle port: numpy "
-                          "callbacks + restated SciPy 2-point FD for eq, ineq and cost; %.1f s of CPU work"
+                          "callbacks + restated SciPy 2-point FD for eq, ineq and cost; best of 3 passes, %.1f s of CPU work each"
                           % (sample, cfg, cpu_s),
                    single_core_value=v_one, **cpu_info())
 

@@ -162,6 +162,8 @@ enum ogb_option {
                                     split into ceil(nvars / cap) items                                 */
     OGB_OPT_AUTO_SPLIT = 7,      /* 1: small batches are cut into more, smaller work items (default 0: the
                                     repeated base-point work cancels the better balance)                  */
+    OGB_OPT_PROBE_MODE = 8,      /* timing probes only (J is NOT a Jacobian afterwards): 2 = no zero stream,
+                                    3 = zero stream only, 4 = no column output at all; 0 = normal             */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
                                     launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
                                     (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */

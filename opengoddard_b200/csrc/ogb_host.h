@@ -45,12 +45,25 @@ static inline size_t ogb_even(size_t x) { return (x + 1) & ~(size_t)1; }
 //   descriptor cache | 2 input stages (p, D.X) | base outputs | c | scalar outs | coef |
 //   prefix | perturbed outputs [max_nouts][G] | dx, x1, dlt, cost [G] | column records [G] |
 //   scalar perturbed outs | cf | rterm | slot table |
-// resident threads per SM the sweep kernel's register budget allows (3 x 256 by default;
-// OGB200_JIT_MINBLOCKS = 4 rebuilds the NVRTC kernel for 64 registers -> 4 x 256)
+// resident threads per SM the sweep kernel's register budget is sized for (65536 registers / budget
+// = registers per thread the NVRTC build may use).  $OGB200_THREAD_BUDGET overrides the default;
+// $OGB200_JIT_MINBLOCKS (older knob) means 256 x k.
+#ifndef OGB_DEFAULT_THREAD_BUDGET
+#define OGB_DEFAULT_THREAD_BUDGET 768
+#endif
 static inline int ogb_thread_budget() {
+    if (const char* tb = getenv("OGB200_THREAD_BUDGET")) {
+        const int v = atoi(tb);
+        if (v >= 64 && v <= 2048) return v;
+    }
     const char* mb = getenv("OGB200_JIT_MINBLOCKS");
-    const int k = mb ? atoi(mb) : 3;
-    return 256 * (k >= 1 && k <= 8 ? k : 3);
+    const int k = mb ? atoi(mb) : 0;
+    return (k >= 1 && k <= 8) ? 256 * k : OGB_DEFAULT_THREAD_BUDGET;
+}
+static inline int ogb_forced_warps() {
+    const char* w = getenv("OGB200_SWEEP_WARPS");
+    const int v = w ? atoi(w) : 0;
+    return (v >= 1 && v <= 8) ? v : 0;
 }
 
 static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, size_t nouts, int warps,
@@ -97,8 +110,9 @@ static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts,
     // pick the CTA size (2..8 warps) that keeps the most warps resident per SM; registers
     // allow 768 threads per SM (<= 85 registers per thread)
     int best_w = 0, best_res = 0;
-    for (int w = 8; w >= 2; w -= 2) {
-        if (force_warps && w != force_warps) continue;
+    if (!force_warps) force_warps = ogb_forced_warps();
+    for (int w = 8; w >= 1; --w) {
+        if (force_warps ? w != force_warps : (w & 1)) continue;
         ogb_layout(P, ncode, nconsts, nouts, w, pl);
         if (pl->smem_bytes > SMEM_MAX) continue;
         int ctas = (int)std::min<size_t>(16, SM_SMEM / (pl->smem_bytes + 1024));

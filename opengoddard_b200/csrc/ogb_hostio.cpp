@@ -268,11 +268,11 @@ int ogb_host_session_stats(void* h, ogb_host_stats* out) {
 int ogb_host_eval_fd(void* h, const double* p_h, const double* lb_h, const double* ub_h, double abs_step,
                      int B, double* c_h, double* J_h, int mode) {
     Session* S = (Session*)h;
+    if (S && B == 0) return 0;
     if (!S || !p_h || !lb_h || !ub_h || !c_h || !J_h) return fail("ogb_host_eval_fd: null argument");
     if (B < 0 || B > S->maxB) return fail("ogb_host_eval_fd: batch larger than the session's max_batch");
     if (mode < OGB_HOST_J_DENSE || mode > OGB_HOST_J_DMA) return fail("ogb_host_eval_fd: unknown mode");
     if (!(abs_step > 0.0)) return fail("ogb_host_eval_fd: abs_step must be positive");
-    if (B == 0) return 0;
     const double t0 = now_ms();
     HCUDA(cudaSetDevice(S->device));
     const int n = S->info.nvars, M = S->info.nrows, CH = S->chunk;

@@ -75,8 +75,11 @@ struct OgbSlot { int rbase, klo, khi, isdyn; };   // where output slot t of a no
 #ifndef OGB_MIN_BLOCKS
 #define OGB_MIN_BLOCKS 3            // resident CTAs per SM the register budget is sized for
 #endif
+#ifndef OGB_MAX_THREADS
+#define OGB_MAX_THREADS 256
+#endif
 template <int NR>
-__global__ void __launch_bounds__(256, OGB_MIN_BLOCKS)
+__global__ void __launch_bounds__(OGB_MAX_THREADS, OGB_MIN_BLOCKS)
 ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const double* __restrict__ DX,
                  const double* __restrict__ lb, const double* __restrict__ ub, double abs_step,
                  int B, double* __restrict__ c, double* __restrict__ J, int with_fd,
@@ -88,9 +91,22 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     P.npick = OGB_SPEC_NPICK; P.has_running = OGB_SPEC_RUNNING; P.sc_nouts = OGB_SPEC_SC_NOUTS;
     P.sc_cost_slot = OGB_SPEC_SC_COST_SLOT; P.max_nouts = OGB_SPEC_MAX_NOUTS;
     pl.G = OGB_SPEC_G;
+#ifdef OGB_SPEC_O_SC                  // ... and so are the offsets of the shared-memory layout
+    pl.o_sbase = OGB_SPEC_O_SBASE; pl.o_sc = OGB_SPEC_O_SC; pl.o_scbase = OGB_SPEC_O_SCBASE;
+    pl.o_coef = OGB_SPEC_O_COEF; pl.o_prefix = OGB_SPEC_O_PREFIX; pl.o_pert = OGB_SPEC_O_PERT;
+    pl.o_pdx = OGB_SPEC_O_PDX; pl.o_px1 = OGB_SPEC_O_PX1; pl.o_pdlt = OGB_SPEC_O_PDLT;
+    pl.o_pcol = OGB_SPEC_O_PCOL; pl.o_scpert = OGB_SPEC_O_SCPERT; pl.o_cf = OGB_SPEC_O_CF;
+    pl.o_rterm = OGB_SPEC_O_RTERM; pl.o_costp = OGB_SPEC_O_COSTP; pl.o_prdx = OGB_SPEC_O_PRDX;
+    pl.o_slot = OGB_SPEC_O_SLOT; pl.o_sp = OGB_SPEC_O_SP; pl.o_sdx = OGB_SPEC_O_SDX;
+    pl.o_cache = OGB_SPEC_O_CACHE; pl.o_end = OGB_SPEC_O_END;
+#endif
 #endif
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    // %laneid through a volatile asm: the compiler keeps it in a register instead of re-reading
+    // SR_TID.X (an S2R costs ~20 cycles) at every use inside the column loop
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = tid >> 5, nwarps = nthr >> 5;
     OgbWork W;
     W.sbase = smem + pl.o_sbase; W.sc = smem + pl.o_sc; W.scbase = smem + pl.o_scbase;
     W.coef = smem + pl.o_coef; W.prefix = smem + pl.o_prefix; W.pert = smem + pl.o_pert;
@@ -234,6 +250,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         }
 
         // ---- phase 2: tapes -- base nodes, scalar program, one job per Jacobian column
+        if (with_fd != 5)        // (probe 5: no tapes, no assembly -- the zero stream alone)
         for (int q = tid; q < P.gtot + 1 + ncols; q += nthr) ogb_job(P, W, q, jlo, lb, ub, abs_step);
         if (tid == 0) *s_next = claimed;
         __syncthreads();
@@ -242,8 +259,8 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
 
         // ---- phase 3: c at the base point and the perturbed cost of every column.  Without a
         //      running cost neither depends on the other, so one barrier covers both.
-        ogb_assemble_base(P, W, tid, nthr);
-        if (!P.has_running) {
+        if (with_fd != 5) ogb_assemble_base(P, W, tid, nthr);
+        if (!P.has_running && with_fd != 5) {
             if (tid == 0) ogb_assemble_cost(P, W);
             for (int cl = tid; cl < ncols; cl += nthr) ogb_cost_column(P, W, cl);
         }
@@ -262,48 +279,60 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         //      16-byte stores, then (ordered by __syncwarp) overwrites the few rows that can be
         //      non-zero.  The overwrites hit sectors still resident in L2, so DRAM sees each
         //      sector once.
+        //      The loop is written for a short dependent chain (the kernel runs at ~0.45 IPC, bound
+        //      by instruction latency, not by HBM): every operand of the column is loaded first
+        //      (shared memory through constant offsets, D^T through the read-only path), the zero
+        //      stream is issued while those loads fly, and the column pointer is carried from
+        //      iteration to iteration instead of being rebuilt from (instance, column) per store.
         {
             constexpr int NRA = NR > 0 ? NR : 1;
-            double* __restrict__ Jb = J + (size_t)b * n * (size_t)M;   // n * M < 2^32 (checked on the host)
-            int cur_sec = -1, cur_blk = -1, slot_sec = -1;
+            double* gdst = J + (size_t)b * n * (size_t)M + (size_t)(jlo + warp) * (size_t)M;
+            const size_t gstep = (size_t)nwarps * (size_t)M;
+            int cur_key = -1, slot_sec = -1;
             double r_sdx[NRA], r_cf[NRA], r_sc[NRA];
             OgbSlot si = {0, 0, 0, 0};               // where this lane's output slot lands (per phase)
-            // Everything a column needs from shared / read-only memory is fetched one column ahead
-            // (software pipeline), so the loads of column c+1 fly while column c streams out.
-            struct ColMeta { OgbCol cd; double dx, rdx, dlt, x1, dkk, pv; double dtv[NRA]; };
-            auto load_meta = [&](int cc, ColMeta& m) {
-                m.cd = W.pcol[cc]; m.dx = W.pdx[cc]; m.rdx = W.prdx[cc]; m.dlt = W.pdlt[cc]; m.x1 = W.px1[cc];
-                m.dkk = 0.0; m.pv = 0.0;
+            const double* const s_pdx = smem + pl.o_pdx;
+            const double* const s_prdx = smem + pl.o_prdx;
+            const double* const s_pdlt = smem + pl.o_pdlt;
+            const double* const s_pert = smem + pl.o_pert;
+            const double* const s_sc = smem + pl.o_sc;
+            const double* const s_cf = smem + pl.o_cf;
+            const double* const s_coef = smem + pl.o_coef;
+            const int4* const s_pcol = reinterpret_cast<const int4*>(smem + pl.o_pcol);
+            const double* const s_sdx = W.sdx;       // (the input stage alternates between items)
+            for (int cc = warp; cc < ncols; cc += nwarps, gdst += gstep) {
+                asm volatile("" : "+l"(gdst));       // keep the column pointer in registers ...
+                __builtin_assume(__isGlobal(gdst));  // ... and its stores in the global space (STG, not ST)
+                // (A) operands
+                const int4 cdv = s_pcol[cc];
+                const OgbCol cd = {cdv.x, cdv.y, cdv.z, cdv.w};
+                const double dx = s_pdx[cc], rdx = s_prdx[cc];
+                const bool fcol = fast && cd.sec >= 0;
+                double dlt = 0.0, pv = 0.0, dkk = 0.0, coef = 0.0;
+                double dtv[NRA];
 #pragma unroll
-                for (int r = 0; r < NRA; ++r) m.dtv[r] = 0.0;
-                if (fast && m.cd.sec >= 0) {
-                    const OgbSec& S = ogb_sec(P, m.cd.sec);
-                    if (m.cd.blk < S.ns) {
-                        const double* __restrict__ Dt = P.Dt + S.doff + m.cd.k * S.N;
+                for (int r = 0; r < NRA; ++r) dtv[r] = 0.0;
+                int a = -1;
+                if (fcol) {
+                    const OgbSec& S = ogb_sec(P, cd.sec);
+                    dlt = s_pdlt[cc];
+                    coef = s_coef[3 * cd.sec];
+                    if (cd.blk < S.ns) {
+                        a = cd.blk;
+                        const double* __restrict__ Dt = P.Dt + S.doff + cd.k * S.N;
 #pragma unroll
                         for (int r = 0; r < NRA; ++r) {
                             const int i = lane + 32 * r;
-                            if (i < S.N) m.dtv[r] = __ldg(Dt + i);
+                            if (i < S.N) dtv[r] = __ldg(Dt + i);
                         }
-                        m.dkk = __ldg(Dt + m.cd.k);
+                        dkk = __ldg(Dt + cd.k);
                     }
-                    if (lane < S.nouts) m.pv = W.pert[lane * W.G + cc];
+                    if (lane < S.nouts) pv = s_pert[lane * W.G + cc];
                 }
-            };
-            ColMeta nxt;
-            if (warp < ncols) load_meta(warp, nxt);
-            for (int cc = warp; cc < ncols; cc += nwarps) {
-                const ColMeta cur = nxt;
-                if (cc + nwarps < ncols) load_meta(cc + nwarps, nxt);
-                const int j = jlo + cc;
-                double* __restrict__ gdst = Jb + (unsigned)j * (unsigned)M;
-                const OgbCol cd = cur.cd;
-                const double dx = cur.dx, rdx = cur.rdx;
-                const bool fcol = fast && cd.sec >= 0;
-                const int a = (fcol && cd.blk < ogb_sec(P, cd.sec).ns) ? cd.blk : -1;
-                if (with_fd != 2) {   // zeros: 16-byte aligned body, an odd first / last double on its own
-                                      // (with_fd == 2: structure probe -- only the overwrites below land,
-                                      //  on a sentinel-filled J; see ogb_jac_pattern)
+                // (B) zeros: 16-byte aligned body, an odd first / last double on its own
+                //     (with_fd == 2: structure probe -- only the overwrites below land, on a
+                //      sentinel-filled J; see ogb_jac_pattern.  3 / 4 / 5: timing probes)
+                if (with_fd != 2 && with_fd != 4) {
                     const unsigned hj = (unsigned)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
                     const unsigned nbytes = ((unsigned)(M - hj) & ~1u) * 8u;
                     char* g = reinterpret_cast<char*>(gdst + hj) + lane * 16;
@@ -324,64 +353,66 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                     if (lane == 1 && ((M - hj) & 1)) gdst[M - 1] = 0.0;
                 }
                 __syncwarp();
+                if (with_fd >= 3) continue;          // timing probes: zero stream only / no column output
+                // (C) the rows that can be non-zero
+                const int j = jlo + cc;
                 const OgbColOut col{gdst, gdst + meq, meq};
                 if (fcol) {
                     const OgbSec& S = ogb_sec(P, cd.sec);
                     const int N = S.N, k = cd.k;
-                    const double dlt = cur.dlt;
                     if (cd.sec != slot_sec) {                    // new phase: this lane's slot record
                         slot_sec = cd.sec;
                         si = lane < S.nouts ? slots[S.out_off + lane] : OgbSlot{0, 0, 0, 0};
                     }
                     if (a >= 0) {
-                        if (cd.sec != cur_sec || cd.blk != cur_blk) {    // new state block: reload row constants
-                            cur_sec = cd.sec; cur_blk = cd.blk;
+                        const int key = cd.sec * 1024 + a;
+                        if (key != cur_key) {                    // new state block: reload row constants
+                            cur_key = key;
 #pragma unroll
                             for (int r = 0; r < NRA; ++r) {
                                 const int i = lane + 32 * r;
                                 if (i < N) {
-                                    r_sdx[r] = W.sdx[S.dxoff + a * N + i];
-                                    r_cf[r] = W.cf[S.dxoff + a * N + i];
-                                    r_sc[r] = W.sc[S.rdef + a * N + i];
+                                    r_sdx[r] = s_sdx[S.dxoff + a * N + i];
+                                    r_cf[r] = s_cf[S.dxoff + a * N + i];
+                                    r_sc[r] = s_sc[S.rdef + a * N + i];
                                 }
                             }
                         }
-                        double* crow = gdst + S.rdef + a * N;
+                        double* crow = gdst + (S.rdef + a * N + lane);
 #pragma unroll
                         for (int r = 0; r < NRA; ++r) {
                             const int i = lane + 32 * r;
                             if (i < N && i != k) {
-                                const double cp = (r_sdx[r] + cur.dtv[r] * dlt) - r_cf[r];
-                                crow[i] = ogb_fd_div(cp - r_sc[r], dx, rdx);
+                                const double cp = (r_sdx[r] + dtv[r] * dlt) - r_cf[r];
+                                crow[32 * r] = ogb_fd_div(cp - r_sc[r], dx, rdx);
                             }
                         }
                     }
-                    const double coef = W.coef[3 * cd.sec];
                     if (k >= si.klo && k < si.khi) {             // slot t = lane (slots 0..31)
-                        double cp = cur.pv;
+                        double cp = pv;
                         const int r = si.rbase + k;
                         if (si.isdyn) {
-                            double dxp = W.sdx[S.dxoff + lane * N + k];
-                            if (lane == a) dxp = dxp + cur.dkk * dlt;
+                            double dxp = s_sdx[S.dxoff + lane * N + k];
+                            if (lane == a) dxp = dxp + dkk * dlt;
                             cp = dxp - coef * cp;
                         }
-                        gdst[r] = ogb_fd_div(cp - W.sc[r], dx, rdx);
+                        gdst[r] = ogb_fd_div(cp - s_sc[r], dx, rdx);
                     }
                     for (int t = lane + 32; t < S.nouts; t += 32) {   // (rare) more than 32 output slots
                         const OgbSlot s2 = slots[S.out_off + t];
                         if (k >= s2.klo && k < s2.khi) {
-                            double cp = W.pert[t * W.G + cc];
+                            double cp = s_pert[t * W.G + cc];
                             const int r = s2.rbase + k;
                             if (s2.isdyn) {
-                                double dxp = W.sdx[S.dxoff + t * N + k];
-                                if (t == a) dxp = dxp + cur.dkk * dlt;
+                                double dxp = s_sdx[S.dxoff + t * N + k];
+                                if (t == a) dxp = dxp + dkk * dlt;
                                 cp = dxp - coef * cp;
                             }
-                            gdst[r] = ogb_fd_div(cp - W.sc[r], dx, rdx);
+                            gdst[r] = ogb_fd_div(cp - s_sc[r], dx, rdx);
                         }
                     }
-                    if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots(P, W, j, cur.x1, dx, rdx, col, lane, 32);
-                    ogb_scatter_scalar_cost(P, W, cd, cc, dx, rdx, col, lane, 32);
+                    if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots(P, W, j, W.px1[cc], dx, rdx, col, lane, 32);
+                    if (cd.pick >= 0 || P.has_running) ogb_scatter_scalar_cost(P, W, cd, cc, dx, rdx, col, lane, 32);
                 } else {
                     ogb_scatter_column(P, W, j, cc, col, lane, 32);
                 }

@@ -205,3 +205,63 @@ def test_solve_batch_multistart(torch_cuda, api, capsys):
     single.prob.solve(single.obj)
     capsys.readouterr()
     assert np.array_equal(np.asarray(single.prob.p), res["x"][0])
+
+
+def test_empty_batch(torch_cuda, api):
+    """B = 0 is a no-op through every entry point (device tensors and host session)."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg2_goddard50", api)
+    eng = wl.prob.compile(wl.obj)
+    n, M = eng.nvars, eng.nrows
+    c, J = eng.eval_fd(np.zeros((0, n)))
+    assert tuple(c.shape) == (0, M) and tuple(J.shape) == (0, n, M)
+    assert tuple(eng.eval(np.zeros((0, n))).shape) == (0, M)
+    S = eng.host_session(4)
+    c, J = S.eval_fd(np.zeros((0, n)))
+    assert c.shape == (0, M) and J.shape == (0, n, M)
+    S.close()
+
+
+def test_bound_adjusted_steps_vs_oracle(torch_cuda, api):
+    """Variables sitting exactly on a bound, within one step of it, and outside it: SciPy flips or
+    shrinks the forward step (_numdiff.py:14-90) and clips x first (_slsqp_py.py:355).  The shipped
+    Goddard script only bounds t_f, so box bounds are put on every block here (same calls on the
+    facade and on the oracle)."""
+    from opengoddard_b200 import workloads
+    from oracle import og_numpy
+    wl = workloads.build("cfg2_goddard50", api)
+    wo = workloads.build("cfg2_goddard50", og_numpy)
+    for prob in (wl.prob, wo.prob):
+        prob.set_states_bounds(0, 0, 1.0, 1.008)               # h
+        prob.set_states_bounds(1, 0, 0.0, None)                # v: lower bound only
+        prob.set_states_bounds(2, 0, 0.6, 1.0)                 # m
+        prob.set_controls_bounds(0, 0, 0.0, 3.0)               # T
+        prob.set_time_final_bounds(0, 0.1, 0.25)
+    lb, ub = og_numpy.bounds_arrays(wo.prob)
+    fin_l, fin_u = np.isfinite(lb), np.isfinite(ub)
+    assert fin_l.sum() > 150 and fin_u.sum() > 100
+    P = workloads.make_batch(wl, 7)
+    P[0, fin_u] = ub[fin_u]                                    # on the upper bound: the step flips
+    P[1, fin_l] = lb[fin_l]                                    # on the lower bound
+    P[2, fin_u] = ub[fin_u] - 0.5e-8                           # closer than one step to the bound
+    P[3, fin_u] = ub[fin_u] + 0.25                             # outside: clipped first
+    P[4, fin_l] = lb[fin_l] - 0.25
+    both = fin_l & fin_u
+    P[5, both] = 0.5 * (lb[both] + ub[both])
+    # instance 6: the jittered guess as generated
+    eng = wl.prob.compile(wl.obj)
+    c, J = eng.eval_fd(P)
+    c, J = c.cpu().numpy(), J.cpu().numpy()
+    S = eng.host_session(8)
+    ch, Jh = S.eval_fd(P)                                      # the session uploads the same bounds
+    assert (ch == c).all() and (Jh == J).all()
+    S.close()
+    checked = 0
+    for b in range(7):
+        c_ref, J_ref = og_numpy.eval_fd(wo.prob, wo.obj, P[b], lb, ub)
+        if not (np.isfinite(c_ref).all() and np.isfinite(J_ref).all()):
+            continue
+        assert_c_close(c[b], c_ref, J_ref, np.clip(P[b], lb, ub))
+        assert_J_close(J[b].T, J_ref)
+        checked += 1
+    assert checked >= 5
