@@ -160,8 +160,8 @@ enum ogb_option {
                                     0: static round-robin assignment                                    */
     OGB_OPT_GROUP_COLS = 6,      /* cap on Jacobian columns per work item (default 256); an instance is
                                     split into ceil(nvars / cap) items                                 */
-    OGB_OPT_AUTO_SPLIT = 7,      /* 1: small batches are cut into more, smaller work items (default 0: the
-                                    repeated base-point work cancels the better balance)                  */
+    OGB_OPT_AUTO_SPLIT = 7,      /* 1 (default): batches with fewer than ~6 instances per resident CTA are cut
+                                    into more, smaller work items (bit-identical results, better balance)  */
     OGB_OPT_PROBE_MODE = 8,      /* timing probes only (J is NOT a Jacobian afterwards): 2 = no zero stream,
                                     3 = zero stream only, 4 = no column output at all; 0 = normal             */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two

@@ -18,6 +18,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -43,6 +44,16 @@ int usable_cores() {
     return std::max(1u, std::thread::hardware_concurrency());
 }
 
+int host_isa() {
+    // $OGB200_HOST_ISA = 0 / 1 / 2 picks SSE2 / AVX2 / AVX-512 stores.  Default AVX2: one core's
+    // non-temporal write rate (~13 GB/s) is the limit either way and 512-bit stores measured slower.
+    const char* f = getenv("OGB200_HOST_ISA");
+    const int cap = f ? atoi(f) : 1;
+    if (cap >= 2 && __builtin_cpu_supports("avx512f")) return 2;
+    if (cap >= 1 && __builtin_cpu_supports("avx2")) return 1;
+    return 0;
+}
+
 // ---------------------------------------------------------------- dense expansion of one instance
 constexpr int kPiece = 512;                      // doubles per L1-resident piece (4 KB)
 
@@ -52,13 +63,20 @@ __attribute__((target("avx2"))) void stream_piece_avx2(double* dst, const double
         _mm256_stream_pd(dst + k + 4, _mm256_load_pd(buf + k + 4));
     }
 }
+__attribute__((target("avx512f"))) void stream_piece_avx512(double* dst, const double* buf) {
+    for (int k = 0; k < kPiece; k += 16) {
+        _mm512_stream_pd(dst + k, _mm512_load_pd(buf + k));
+        _mm512_stream_pd(dst + k + 8, _mm512_load_pd(buf + k + 8));
+    }
+}
 void stream_piece_sse2(double* dst, const double* buf) {
     for (int k = 0; k < kPiece; k += 2) _mm_stream_pd(dst + k, _mm_load_pd(buf + k));
 }
 
 // dst[0, nM) = 0 except dst[lin[e]] = vals[e]; lin ascending.  The body is produced piece by
 // piece in an L1 buffer and streamed out with non-temporal stores (no read-for-ownership).
-void expand_dense(double* dst, size_t nM, const double* vals, const uint32_t* lin, int nnz, bool avx2) {
+// isa: 2 = AVX-512, 1 = AVX2, 0 = SSE2 non-temporal stores
+void expand_dense(double* dst, size_t nM, const double* vals, const uint32_t* lin, int nnz, int isa) {
     alignas(64) double buf[kPiece];
     size_t pos = 0;
     int e = 0;
@@ -70,7 +88,9 @@ void expand_dense(double* dst, size_t nM, const double* vals, const uint32_t* li
         const int e0 = e;
         const size_t end = pos + kPiece;
         while (e < nnz && lin[e] < end) { buf[lin[e] - pos] = vals[e]; ++e; }
-        if (avx2) stream_piece_avx2(dst + pos, buf); else stream_piece_sse2(dst + pos, buf);
+        if (isa == 2) stream_piece_avx512(dst + pos, buf);
+        else if (isa == 1) stream_piece_avx2(dst + pos, buf);
+        else stream_piece_sse2(dst + pos, buf);
         for (int q = e0; q < e; ++q) buf[lin[q] - pos] = 0.0;       // re-zero only what was touched
         pos = end;
     }
@@ -91,7 +111,7 @@ struct Job {
     const uint32_t* lin = nullptr;
     int nnz = 0, M = 0, B = 0, chunk = 1, mode = 0;
     size_t nM = 0;
-    bool avx2 = false;
+    int isa = 0;
 };
 
 class Pool {
@@ -118,7 +138,7 @@ public:
         if (j.c_dst) std::memcpy(j.c_dst + (size_t)b * j.M, j.c_src + (size_t)b * j.M, (size_t)j.M * sizeof(double));
         if (!j.vals) return;
         const double* v = j.vals + (size_t)b * j.nnz;
-        if (j.mode == OGB_HOST_J_DENSE) expand_dense(j.J_dst + (size_t)b * j.nM, j.nM, v, j.lin, j.nnz, j.avx2);
+        if (j.mode == OGB_HOST_J_DENSE) expand_dense(j.J_dst + (size_t)b * j.nM, j.nM, v, j.lin, j.nnz, j.isa);
         else if (j.mode == OGB_HOST_J_KEEP_ZEROS) expand_keep(j.J_dst + (size_t)b * j.nM, v, j.lin, j.nnz);
         else std::memcpy(j.J_dst + (size_t)b * j.nnz, v, (size_t)j.nnz * sizeof(double));
     }
@@ -171,7 +191,7 @@ struct Session {
     int nnz = 0;
     size_t nM = 0;
     std::vector<uint32_t> lin;
-    bool avx2 = false;
+    int isa = 0;
     // device
     double *p_d = nullptr, *lb_d = nullptr, *ub_d = nullptr, *c_d = nullptr, *vals_d = nullptr;
     double *J_d = nullptr, *DX_d = nullptr, *Jfull_d = nullptr;
@@ -219,7 +239,7 @@ int session_init(Session* S, void* prob, int max_batch, int chunk, int threads) 
     }
     S->chunk = std::min(chunk, max_batch);
     S->nchunks = (max_batch + S->chunk - 1) / S->chunk;
-    S->avx2 = __builtin_cpu_supports("avx2");
+    S->isa = host_isa();
     const size_t B = (size_t)max_batch;
     HCUDA(cudaMalloc((void**)&S->p_d, B * n * 8));
     HCUDA(cudaMalloc((void**)&S->lb_d, (size_t)n * 8));
@@ -294,7 +314,7 @@ int ogb_host_eval_fd(void* h, const double* p_h, const double* lb_h, const doubl
     Job job;
     job.vals = dma ? nullptr : S->vals_s;
     job.c_src = S->c_s; job.c_dst = c_h; job.J_dst = J_h; job.lin = S->lin.data();
-    job.nnz = S->nnz; job.M = M; job.B = B; job.chunk = CH; job.mode = mode; job.nM = S->nM; job.avx2 = S->avx2;
+    job.nnz = S->nnz; job.M = M; job.B = B; job.chunk = CH; job.mode = mode; job.nM = S->nM; job.isa = S->isa;
     S->pool->start(job);
 
     int rc = 0;
@@ -356,7 +376,7 @@ int ogb_host_expand(const double* vals_h, const uint32_t* lin_h, int nnz, size_t
     threads = std::max(1, std::min(threads, std::max(1, B)));
     Job j;
     j.vals = vals_h; j.J_dst = J_h; j.lin = lin_h; j.nnz = nnz; j.B = B; j.chunk = std::max(1, B); j.mode = mode;
-    j.nM = nM; j.avx2 = __builtin_cpu_supports("avx2");
+    j.nM = nM; j.isa = host_isa();
     std::atomic<int> next{0};
     auto work = [&] { for (int b; (b = next.fetch_add(1)) < B;) Pool::run_one(j, b); };
     std::vector<std::thread> th;

@@ -291,6 +291,7 @@ class _HostEvaluator:
 
     def __init__(self, eng):
         self.eng = eng
+        self.session = None
 
     def eval(self, X):
         t = self.eng.torch
@@ -298,9 +299,15 @@ class _HostEvaluator:
         return c.cpu().numpy()
 
     def eval_fd(self, X):
-        t = self.eng.torch
-        c, J = self.eng.eval_fd(t.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.eng.device))
-        return c.cpu().numpy(), J.cpu().numpy()
+        """c (k, M) and the dense J (k, n, M) in host memory through the host-buffer session
+        (packed device->host transport, ogb_host_eval_fd)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        k = X.shape[0]
+        if self.session is None or self.session.max_batch < k:
+            if self.session is not None:
+                self.session.close()
+            self.session = self.eng.host_session(max(k, 16))
+        return self.session.eval_fd(X, mode="dense")
 
 
 def lgl_device(N, device="cuda:0"):
