@@ -323,6 +323,29 @@ def main():
     total_ms = float(total_ms.item())
     value = world * B * args.steps / (total_ms * 1e-3)
 
+    # ---- the one exchange step of the path: all-gather of the per-instance
+    #      decision vectors and costs over NCCL, outside the timed steps, reported on its own
+    gather = None
+    if dist is not None:
+        from opengoddard_b200 import batch as ogb_batch
+        cost = c[:, M - 1].contiguous()
+        for _ in range(2):
+            ogb_batch.gather_rows(P, world * B)
+            ogb_batch.gather_rows(cost, world * B)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        allP = ogb_batch.gather_rows(P, world * B)
+        allcost = ogb_batch.gather_rows(cost, world * B)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        assert allP.shape[0] == world * B and torch.equal(allP[rank * B:(rank + 1) * B], P)
+        gather = {"what": "all-gather of p (B x nvars) and cost (B) from every rank (NCCL), after the timed steps",
+                  "ms": float(gms.item()), "bytes_per_rank": int(P.numel() * 8 + cost.numel() * 8)}
+        del allP, allcost
+
     # ---- end to end through the host-buffer C-ABI entry point (ogb_host_eval_fd): p in pinned HOST
     #      memory in, c and the dense J in HOST memory out, every copy inside the timed region.
     #      The call is synchronous and its last stage runs on host threads, so the clock is the
@@ -410,6 +433,8 @@ def main():
                          "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
+        if gather is not None:
+            out["gather"] = gather
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()

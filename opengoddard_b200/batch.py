@@ -42,3 +42,46 @@ def gather_rows(local, total, group=None):
     dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
     pieces = [out[r * cap:r * cap + sizes[r]] for r in range(world)]
     return torch.cat(pieces, dim=0)
+
+
+def run_sharded(fn, rows, group=None, device=None):
+    """Data-parallel driver of the instance axis: this rank runs `fn` on its contiguous slice of
+    `rows` (numpy, (B, ...)) and every per-instance result is all-gathered, so all ranks return
+    the same dict as a single process calling fn(rows) would (instances are independent, so the
+    entries are bitwise identical to the unsharded run).  `fn` returns a dict of numpy arrays /
+    lists with one entry per local instance.  Without an initialised process group (or with one
+    rank) this is fn(rows).  `device`: where the collective runs (a CUDA device for NCCL, None =
+    CPU for gloo)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return fn(rows)
+    total = len(rows)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_range(total, rank, world)
+    local = fn(rows[lo:hi])
+    out = {}
+    for key in sorted(local):
+        val = local[key]
+        if isinstance(val, (list, tuple)):                  # e.g. exit messages: gather as objects
+            parts = [None] * world
+            dist.all_gather_object(parts, list(val), group=group)
+            out[key] = [v for part in parts for v in part]
+            continue
+        arr = np.ascontiguousarray(val)
+        t = torch.from_numpy(arr)
+        if device is not None:
+            t = t.to(device)
+        out[key] = gather_rows(t, total, group=group).cpu().numpy()
+    return out
+
+
+def best_instance(result):
+    """Index of the converged instance (exit mode 0) with the lowest cost, or of the lowest cost
+    overall if none converged -- the multi-start pick."""
+    import numpy as np
+    fun = np.asarray(result["fun"], dtype=float)
+    ok = np.asarray(result["status"]) == 0
+    cand = np.where(ok, fun, np.inf) if ok.any() else fun
+    return int(np.argmin(cand))

@@ -160,7 +160,10 @@ class DeviceProblem:
         return c, J
 
     def host_evaluator(self):
-        return _HostEvaluator(self)
+        """numpy-in / numpy-out evaluator for sqp.slsqp_batch (one per engine: it owns a host session)."""
+        if getattr(self, "_host_eval", None) is None:
+            self._host_eval = _HostEvaluator(self)
+        return self._host_eval
 
     def host_session(self, max_batch, chunk=0, threads=0):
         """Host-buffer entry point (ogb_host_eval_fd): numpy / pinned host arrays in and out."""

@@ -326,24 +326,37 @@ class Problem:
         eng = self._engine if self._engine is not None else self.compile(obj)
         return eng.eval_fd(P) if jacobian else eng.eval(P)
 
-    def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1):
+    def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None):
         """Multi-start: solve the NLP from every row of P0 (B, nvars) at once.
+
+        Under an initialised torch.distributed process group (one rank per GPU) the rows of P0
+        are sharded contiguously over the ranks, each rank solves its slice on its own GPU with no
+        communication, and the per-instance results are all-gathered at the end (NCCL), so every
+        rank returns the full result (batch.run_sharded).
 
         Every instance runs SciPy's SLSQP state machine (same C core as `solve`); all function
         and Jacobian evaluations of an SQP step are served by one batched device call
         (sqp.slsqp_batch).  Like `solve` (reference optimize.py:738-755) instances that did not
         reach exit mode 0 are restarted from where they stopped, up to `max_outer`
         (default maxIterator) times.  Returns dict(x, fun, status, nit, outer)."""
-        from . import sqp
+        from . import batch, sqp
         self._check_callbacks()
         eng = self._engine if self._engine is not None else self.compile(obj)
+        P0 = np.array(np.atleast_2d(P0), dtype=np.float64)
+        return batch.run_sharded(
+            lambda rows: self._solve_rows(eng, rows, obj, ftol, maxiter, max_outer, threads, sqp),
+            P0, group=group, device=eng.device)
+
+    def _solve_rows(self, eng, P0, obj, ftol, maxiter, max_outer, threads, sqp):
         lb, ub = self.bounds_arrays()
-        X = np.array(np.atleast_2d(P0), dtype=np.float64)
+        X = np.array(np.atleast_2d(P0), dtype=np.float64).reshape(-1, self.number_of_variables)
         B = X.shape[0]
         status = np.full(B, 9)
         fun = np.zeros(B)
         nit = np.zeros(B, dtype=int)
         outer = np.zeros(B, dtype=int)
+        if B == 0:                                          # an empty shard (fewer starts than ranks)
+            return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
         grad = None
         if self.cost_derivative is not None:
             def grad(x):

@@ -80,3 +80,59 @@ def test_gather_rows_gloo_world2():
 def test_gather_rows_single_process_passthrough():
     x = torch.arange(12.0).reshape(4, 3)
     assert batch.gather_rows(x, 4) is x
+
+
+def _solve_worker(rank, world, port, total, out):
+    import torch.distributed as dist
+    from opengoddard_b200 import sqp
+    from tests.test_sqp import OracleEvaluator
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+        ev = OracleEvaluator(wl)
+        P = workloads.make_batch(wl, total)                # every rank holds the full start set
+
+        def solve(rows):                                   # the oracle stands in for the device evaluator
+            if len(rows) == 0:
+                return {"x": rows.reshape(0, P.shape[1]), "fun": np.zeros(0), "status": np.zeros(0, dtype=int),
+                        "message": []}
+            r = sqp.slsqp_batch(ev, rows, ev.lb, ev.ub, 64, 41, ftol=1e-6, maxiter=4)
+            return {"x": r["x"], "fun": r["fun"], "status": r["status"], "message": r["message"]}
+
+        res = batch.run_sharded(solve, P)
+        out.put((rank, res["x"], res["fun"], res["status"], res["message"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [5, 1])
+def test_run_sharded_matches_the_single_process_run(total):
+    """world_size 2 over gloo: sharded multi-start == unsharded, bit for bit, on every rank
+    (total = 1 leaves rank 1 with an empty shard)."""
+    from opengoddard_b200 import sqp
+    from tests.test_sqp import OracleEvaluator
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_solve_worker, args=(r, world, port, total, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    ev = OracleEvaluator(wl)
+    ref = sqp.slsqp_batch(ev, workloads.make_batch(wl, total), ev.lb, ev.ub, 64, 41, ftol=1e-6, maxiter=4)
+    for rank, x, fun, status, message in got:
+        assert np.array_equal(x, ref["x"]) and np.array_equal(fun, ref["fun"])
+        assert np.array_equal(status, ref["status"]) and message == ref["message"]
+    assert batch.best_instance({"fun": ref["fun"], "status": ref["status"]}) == int(np.argmin(ref["fun"]))
+
+
+def test_best_instance_prefers_converged_starts():
+    assert batch.best_instance({"fun": [3.0, 1.0, 2.0], "status": [0, 9, 0]}) == 2
+    assert batch.best_instance({"fun": [3.0, 1.0, 2.0], "status": [9, 9, 9]}) == 1

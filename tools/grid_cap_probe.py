@@ -17,7 +17,7 @@ DX = eng.dx_gemm(P, clip=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 bpe = 8 * eng.nvars + 8 * eng.nrows * (eng.nvars + 1)
 slots = 148 * eng.info.ctas_per_sm
-caps = [0] + sorted({-(-B // r) for r in range(max(1, B // slots), B // slots + 8)}, reverse=True)
+caps = [0, -1] + sorted({-(-B // r) for r in range(max(1, B // slots), B // slots + 8)}, reverse=True)
 for cap in caps:
     eng.set_option(3, cap)
     for _ in range(3):
@@ -31,4 +31,4 @@ for cap in caps:
         ts.append(e0.elapsed_time(e1))
     ms = sum(ts) / len(ts)
     print("grid cap %4d (%.2f items per CTA): avg %.3f ms min %.3f  %.0f GB/s" % (
-        cap, B / (cap or slots), ms, min(ts), B * bpe / ms / 1e6))
+        cap, B / (cap if cap > 0 else (slots if cap == 0 else B)), ms, min(ts), B * bpe / ms / 1e6))
