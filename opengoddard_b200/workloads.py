@@ -841,3 +841,80 @@ def table_lookup(api, nodes=(12, 9)):
 
 
 CONFIGS["edge_table_lookup"] = (table_lookup, (12, 9))
+
+
+def all_ops(api, nodes=(9, 6)):
+    """Edge case: every numpy ufunc / operator the tracer accepts that no other workload uses
+    (tan, arcsin, arccos, arctan, sinh, log, log10, sign, floor, ceil, square, reciprocal, fabs,
+    minimum, maximum, fmin, fmax, non-integer and negative powers, scalar ** array, comparisons,
+    logical_and / or / not, unary minus / plus, deg2rad) in dynamics, point rows, scalar rows, the
+    cost and a running cost -- smooth arguments only, so the forward differences are well defined."""
+    class Par:
+        a, b = 0.8, 1.7
+
+    par = Par()
+    prob = api.Problem([0.0, 2.0, 3.0], list(nodes), [3, 3], [2, 2], 3)
+    prob.set_unit_states_all_section(1, 3.0)
+    prob.set_unit_controls_all_section(1, 0.5)
+    prob.set_unit_time(1.5)
+
+    def dyn(prob, obj, section):
+        x = prob.states(0, section)          # in (0.2, 0.9)
+        y = prob.states(1, section)          # in (1, 3)
+        z = prob.states(2, section)          # in (-0.6, 0.6)
+        u = prob.controls(0, section)
+        w = prob.controls(1, section)
+        d = api.Dynamics(prob, section)
+        d[0] = np.tan(0.5 * x) + np.arcsin(z) * np.arccos(0.5 * z) - np.sinh(z) + np.log(y) * np.log10(1.0 + y)
+        d[1] = (np.minimum(u, 0.3 * y) + np.maximum(w, -x) + np.fmin(x, 0.95) * np.fmax(z, -0.9)
+                + np.square(x) * np.reciprocal(y) + np.fabs(z - 2.0) + y ** 0.5 + y ** -1.5 + 2.0 ** x
+                + np.power(y, obj.a))
+        d[2] = (np.arctan(obj.b * z) + np.sign(y) * np.floor(y + 10.25) * 0.01 + np.ceil(x - 7.5) * 0.02
+                + np.where(np.logical_and(x > 0.0, y >= 0.5), -z, +z)
+                + np.where(np.logical_or(x < -1.0, np.logical_not(y <= 100.0)), 5.0, np.deg2rad(u))
+                + np.where(np.not_equal(x, 12.0), 1.0, 0.0) * np.where(np.equal(y, -3.0), 2.0, w))
+        return d()
+
+    def eq(prob, obj):
+        r = api.Condition()
+        r.equal(prob.states(0, 0)[0], 0.3)
+        r.equal(np.log(prob.states(1, 0)[0]), np.log(1.5), unit=2.0)
+        r.equal(np.tan(prob.states(2, 0)[0]), 0.0)
+        r.equal(prob.states(0, 1)[0], prob.states(0, 0)[-1])
+        r.equal(prob.states(1, 1)[0] ** 1.5, prob.states(1, 0)[-1] ** 1.5)
+        r.equal(np.arctan(prob.states(2, 1)[0]), np.arctan(prob.states(2, 0)[-1]))
+        return r()
+
+    def ineq(prob, obj):
+        r = api.Condition()
+        r.lower_bound(np.log10(prob.states_all_section(1)), -1.0)
+        r.upper_bound(np.sinh(prob.states_all_section(2)), 4.0)
+        r.lower_bound(np.minimum(prob.controls_all_section(0), 1.0), -2.0)
+        r.upper_bound(np.maximum(prob.time_final(0), 0.5), 9.0, unit=prob.unit_time)
+        return r()
+
+    def cost(prob, obj):
+        return np.arcsin(0.5 * prob.states(2, 1)[-1]) + prob.time_final(-1) ** 1.25
+
+    def running(prob, obj):
+        return 0.1 * np.square(prob.controls_all_section(0)) + 0.01 * np.tan(0.3 * prob.states_all_section(0))
+
+    t = prob.time_all_section
+    G = api.Guess
+    prob.set_states_all_section(0, G.linear(t, 0.3, 0.8))
+    prob.set_states_all_section(1, G.cubic(t, 1.5, 0.2, 2.6, 0.0))
+    prob.set_states_all_section(2, G.linear(t, -0.4, 0.5))
+    prob.set_controls_all_section(0, G.linear(t, 0.2, 0.6))
+    prob.set_controls_all_section(1, G.constant(t, 0.3))
+    prob.set_states_bounds_all_section(0, 0.05, 0.95)
+    prob.set_states_bounds_all_section(2, -0.9, 0.9)
+    prob.dynamics = [dyn, dyn]
+    prob.knot_states_smooth = [False]
+    prob.cost = cost
+    prob.running_cost = running
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("all_ops", prob, par, None)
+
+
+CONFIGS["edge_all_ops"] = (all_ops, (9, 6))

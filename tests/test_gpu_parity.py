@@ -48,7 +48,7 @@ def test_eval_fd_vs_reference_golden(torch_cuda, api, name):
 
 
 @pytest.mark.parametrize("name", ["cfg3_goddard_knot30x2", "cfg4_polar3x40", "cfg5_lowthrust128",
-                                  "edge_table_lookup", "edge_stress_mixed"])
+                                  "edge_table_lookup", "edge_stress_mixed", "edge_all_ops"])
 def test_jit_and_interpreter_kernels_agree(torch_cuda, api, name):
     from opengoddard_b200 import workloads
     wl = workloads.build(name, api)
@@ -88,7 +88,7 @@ def test_dx_gemm_tensor_core(torch_cuda, api, name):
 @pytest.mark.parametrize("name,B", [("cfg2_goddard50", 64), ("cfg3_goddard_knot30x2", 33),
                                     ("cfg5_lowthrust128", 9), ("cfg4_polar3x40", 7),
                                     ("edge_two_stage_no_inequality", 5), ("edge_stress_mixed", 3),
-                                    ("edge_stress_small", 1), ("edge_table_lookup", 6)])
+                                    ("edge_stress_small", 1), ("edge_table_lookup", 6), ("edge_all_ops", 4)])
 def test_batch_vs_oracle(torch_cuda, api, name, B):
     """Seeded jittered batch: CUDA path vs the numpy oracle on the same inputs (odd batch
     sizes exercise the unaligned TMA head/tail handling)."""
