@@ -28,7 +28,8 @@ struct OgbHostProblem {
     std::vector<ogb_table> tables;
     std::vector<double> tab_x, tab_y;
     OgbProb P;          // pointer members reference the vectors above (host view)
-    OgbPlan plan;
+    OgbPlan plan;            // launch plan of the ahead-of-time (tape-interpreter) sweep kernel
+    OgbPlan plan_jit;        // ... of the NVRTC build: the tapes are code there, not shared-memory data
     std::string error;
 
     void bind_host() {
@@ -310,5 +311,6 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
 
     H->bind_host();
     if (!ogb_make_plan(P, H->code.size(), H->consts.size(), H->outs.size(), &H->plan, err)) { delete H; return nullptr; }
+    if (!ogb_make_plan(P, 0, 0, H->outs.size(), &H->plan_jit, err)) { delete H; return nullptr; }
     return H;
 }
