@@ -64,7 +64,7 @@ static inline int ogb_thread_budget() {
 static inline int ogb_forced_warps() {
     const char* w = getenv("OGB200_SWEEP_WARPS");
     const int v = w ? atoi(w) : 0;
-    return (v >= 1 && v <= 8) ? v : 0;
+    return (v >= 1 && v <= 16) ? v : 0;
 }
 
 static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, size_t nouts, int warps,
@@ -112,7 +112,7 @@ static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts,
     // allow 768 threads per SM (<= 85 registers per thread)
     int best_w = 0, best_res = 0;
     if (!force_warps) force_warps = ogb_forced_warps();
-    for (int w = 8; w >= 1; --w) {
+    for (int w = std::max(8, force_warps); w >= 1; --w) {
         if (force_warps ? w != force_warps : (w & 1)) continue;
         ogb_layout(P, ncode, nconsts, nouts, w, pl);
         if (pl->smem_bytes > SMEM_MAX) continue;

@@ -88,3 +88,40 @@ def test_jit_source_compiles_for_sm100a_without_a_gpu(api, name):
     assert nbytes > 10000
     assert "ogb_jit_node_0" in src and "ogb_jit_scalar" in src
     assert ("exp(" in src) if name != "edge_all_ops" else all(f in src for f in ("tan(", "asin(", "log10(", "floor(", "pow("))
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure and /root/reference does not exist on the GPU box: neither may
+    be referenced by the product packages, bench.py's CUDA arm or the C sources."""
+    import ast
+    import glob
+    pkg = glob.glob(os.path.join(ROOT, "opengoddard_b200", "*.py")) + glob.glob(os.path.join(ROOT, "OpenGoddard", "*.py"))
+    assert len(pkg) >= 10
+    for path in pkg:
+        tree = ast.parse(open(path).read())
+        docstrings = set()                                 # citations of reference file:line live in docstrings
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.Module, ast.FunctionDef, ast.ClassDef, ast.AsyncFunctionDef)) and node.body and \
+                    isinstance(node.body[0], ast.Expr) and isinstance(node.body[0].value, ast.Constant):
+                docstrings.add(id(node.body[0].value))
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] in ("oracle", "tests") for n in names), "%s imports %s" % (path, names)
+            if isinstance(node, ast.Constant) and isinstance(node.value, str) and id(node) not in docstrings:
+                assert "/root/reference" not in node.value, "%s uses the reference tree at run time" % path
+    for path in glob.glob(os.path.join(ROOT, "opengoddard_b200", "csrc", "*")) + [HEADER]:
+        if path.endswith(".inc"):
+            continue
+        text = open(path).read()
+        assert "#include \"../../oracle" not in text and "oracle/" not in text.replace("// oracle", "")
+    # in a fresh interpreter, importing the facade and the engine does not pull the oracle in
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import OpenGoddard.optimize, opengoddard_b200.engine, "
+            "opengoddard_b200.sqp, opengoddard_b200.batch; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True, timeout=300)
