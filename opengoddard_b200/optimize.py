@@ -326,7 +326,7 @@ class Problem:
         eng = self._engine if self._engine is not None else self.compile(obj)
         return eng.eval_fd(P) if jacobian else eng.eval(P)
 
-    def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None):
+    def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None, processes=0):
         """Multi-start: solve the NLP from every row of P0 (B, nvars) at once.
 
         Under an initialised torch.distributed process group (one rank per GPU) the rows of P0
@@ -338,16 +338,18 @@ class Problem:
         and Jacobian evaluations of an SQP step are served by one batched device call
         (sqp.slsqp_batch).  Like `solve` (reference optimize.py:738-755) instances that did not
         reach exit mode 0 are restarted from where they stopped, up to `max_outer`
-        (default maxIterator) times.  Returns dict(x, fun, status, nit, outer)."""
+        (default maxIterator) times.  `processes` > 1 steps the per-instance SLSQP cores in that many
+        worker processes (SciPy's step holds the GIL, so this is what makes the host side scale with
+        the cores; sqp._ProcessStepper).  Returns dict(x, fun, status, nit, outer)."""
         from . import batch, sqp
         self._check_callbacks()
         eng = self._engine if self._engine is not None else self.compile(obj)
         P0 = np.array(np.atleast_2d(P0), dtype=np.float64)
         return batch.run_sharded(
-            lambda rows: self._solve_rows(eng, rows, obj, ftol, maxiter, max_outer, threads, sqp),
+            lambda rows: self._solve_rows(eng, rows, obj, ftol, maxiter, max_outer, threads, sqp, processes),
             P0, group=group, device=eng.device)
 
-    def _solve_rows(self, eng, P0, obj, ftol, maxiter, max_outer, threads, sqp):
+    def _solve_rows(self, eng, P0, obj, ftol, maxiter, max_outer, threads, sqp, processes=0):
         lb, ub = self.bounds_arrays()
         X = np.array(np.atleast_2d(P0), dtype=np.float64).reshape(-1, self.number_of_variables)
         B = X.shape[0]
@@ -367,7 +369,7 @@ class Problem:
             if ids.size == 0:
                 break
             res = sqp.slsqp_batch(eng.host_evaluator(), X[ids], lb, ub, eng.meq, eng.mineq, ftol=ftol,
-                                  maxiter=maxiter, cost_grad=grad, threads=threads)
+                                  maxiter=maxiter, cost_grad=grad, threads=threads, processes=processes)
             X[ids] = res["x"]
             status[ids] = res["status"]
             fun[ids] = res["fun"]

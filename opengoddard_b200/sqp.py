@@ -66,18 +66,241 @@ class _Instance:
         return self.state["mode"]
 
 
+class _LocalStepper:
+    """All SLSQP states in this process; the QP cores are stepped one after the other (SciPy's
+    low-level step holds the GIL, so Python threads do not overlap them)."""
+
+    def __init__(self, X0, n, m, meq, acc, maxiter, xl, xu, threads=1):
+        slsqp, ilp64 = _low_level()
+        self._slsqp, self.m, self.xl, self.xu = slsqp, m, xl, xu
+        self.inst = [_Instance(x, n, m, meq, acc, maxiter, np.int64 if ilp64 else np.int32) for x in X0]
+        self.pool = ThreadPoolExecutor(threads) if threads > 1 else None
+
+    def put_values(self, ids, c):
+        m = self.m
+        for k, b in enumerate(ids):
+            it = self.inst[b]
+            it.fx = float(c[k, m])
+            it.d[:m] = c[k, :m]
+
+    def put_normals(self, ids, J, G):
+        m = self.m
+        for k, b in enumerate(ids):
+            it = self.inst[b]
+            it.C[:m, :] = J[k, :, :m].T
+            it.g[:] = G[k] if G is not None else J[k, :, m]
+
+    def _step(self, b):
+        it = self.inst[b]
+        self._slsqp(it.state, it.fx, it.g, it.C, it.d, it.x, it.mult, self.xl, self.xu, it.buffer, it.indices)
+
+    def step(self, active):
+        if self.pool is not None:
+            list(self.pool.map(self._step, active))
+        else:
+            for b in active:
+                self._step(b)
+
+    def x(self, b):
+        return self.inst[b].x
+
+    def mode(self, b):
+        return self.inst[b].state["mode"]
+
+    def iters(self, b):
+        return self.inst[b].state["iter"]
+
+    def fx(self, b):
+        return self.inst[b].fx
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.shutdown()
+
+
+def _worker_loop(conn):
+    """Body of a worker process of _ProcessStepper (entry point: python -m opengoddard_b200.sqp_worker):
+    owns the SLSQP state of its instances; X, c, J, G, mode and iteration counters live in shared
+    memory created by the parent."""
+    from multiprocessing import shared_memory
+    slsqp, ilp64 = _low_level()
+    names, shapes, owned, n, m, meq, acc, maxiter, xl, xu = conn.recv()
+    shms = {k: shared_memory.SharedMemory(name=v) for k, v in names.items()}
+    try:                                   # the parent owns (and unlinks) the segments: attaching must not
+        from multiprocessing import resource_tracker     # register them with this process' tracker (< 3.13)
+        for sh in shms.values():
+            resource_tracker.unregister(sh._name, "shared_memory")
+    except Exception:
+        pass
+    arr = {k: np.ndarray(shapes[k][0], dtype=shapes[k][1], buffer=shms[k].buf) for k in names}
+    inst = {b: _Instance(arr["X"][b], n, m, meq, acc, maxiter, np.int64 if ilp64 else np.int32) for b in owned}
+    conn.send("ready")
+    try:
+        while True:
+            msg = conn.recv()
+            if msg[0] == "stop":
+                break
+            _, vals, norms, use_g, active = msg
+            for b in vals:
+                it = inst[b]
+                it.fx = float(arr["D"][b, m])
+                it.d[:m] = arr["D"][b, :m]
+            for b in norms:
+                it = inst[b]
+                it.C[:m, :] = arr["J"][b, :, :m].T
+                it.g[:] = arr["G"][b] if use_g else arr["J"][b, :, m]
+            for b in active:
+                it = inst[b]
+                slsqp(it.state, it.fx, it.g, it.C, it.d, it.x, it.mult, xl, xu, it.buffer, it.indices)
+                arr["X"][b] = it.x
+                arr["mode"][b] = it.state["mode"]
+                arr["iter"][b] = it.state["iter"]
+                arr["fx"][b] = it.fx
+            conn.send("done")
+    finally:
+        del arr, inst
+        for sh in shms.values():
+            sh.close()
+
+
+class _ProcessStepper:
+    """The SLSQP states are spread over worker PROCESSES (instance b belongs to worker b mod W), so
+    the QP cores of a lock-step round run in parallel on the host cores; decision vectors,
+    constraint values and Jacobians are exchanged through shared memory.  Same arithmetic per
+    instance as _LocalStepper (the instances are independent).  The workers are plain
+    `python -m opengoddard_b200.sqp_worker` subprocesses connected over a local socket -- not
+    multiprocessing children -- so an unguarded user script (the reference's examples have no
+    `if __name__ == "__main__"`) is never re-executed and no CUDA context is forked."""
+
+    def __init__(self, X0, n, m, meq, acc, maxiter, xl, xu, processes):
+        import os
+        import secrets
+        import subprocess
+        import sys
+        import tempfile
+        from multiprocessing import connection, shared_memory
+        B = len(X0)
+        self.m, self.B, self.W = m, B, max(1, min(int(processes), B))
+        shapes = {"X": ((B, n), np.float64), "D": ((B, m + 1), np.float64), "J": ((B, n, m + 1), np.float64),
+                  "G": ((B, n), np.float64), "mode": ((B,), np.int64), "iter": ((B,), np.int64),
+                  "fx": ((B,), np.float64)}
+        self.shms, self.arr, self.conns, self.procs = {}, {}, [], []
+        self._vals, self._norms, self._use_g = [], [], False
+        self._dir = tempfile.mkdtemp(prefix="ogb200_sqp_")
+        try:
+            for k, (shape, dt) in shapes.items():
+                nbytes = max(8, int(np.prod(shape)) * np.dtype(dt).itemsize)
+                self.shms[k] = shared_memory.SharedMemory(create=True, size=nbytes)
+                self.arr[k] = np.ndarray(shape, dtype=dt, buffer=self.shms[k].buf)
+                self.arr[k][...] = 0
+            self.arr["X"][...] = X0
+            names = {k: v.name for k, v in self.shms.items()}
+            key = secrets.token_bytes(16)
+            address = os.path.join(self._dir, "sock")
+            root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            # one BLAS thread per worker: W workers already fill the cores.  (SLSQP's LAPACK calls round
+            # differently with a threaded BLAS, so the result is bitwise the one a single process
+            # produces under OMP_NUM_THREADS=1 / threadpoolctl.threadpool_limits(1).)
+            env = dict(os.environ, OGB200_SQP_KEY=key.hex(), OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1",
+                       MKL_NUM_THREADS="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+            with connection.Listener(address, family="AF_UNIX", authkey=key) as listener:
+                for w in range(self.W):
+                    self.procs.append(subprocess.Popen([sys.executable, "-m", "opengoddard_b200.sqp_worker", address],
+                                                       env=env, stdin=subprocess.DEVNULL))
+                listener._listener._socket.settimeout(120.0)
+                for w in range(self.W):
+                    conn = listener.accept()
+                    conn.send((names, shapes, list(range(w, B, self.W)), n, m, meq, acc, maxiter, xl, xu))
+                    self.conns.append(conn)
+            for w in range(self.W):
+                self._wait(w, "ready")
+        except Exception:
+            self.close()
+            raise
+
+    def _wait(self, w, what, timeout=600.0):
+        conn, waited = self.conns[w], 0.0
+        while not conn.poll(0.5):
+            waited += 0.5
+            if any(pr.poll() is not None for pr in self.procs):
+                raise RuntimeError("an SLSQP worker process exited unexpectedly")
+            if waited >= timeout:
+                raise RuntimeError("SLSQP worker process %d did not answer within %g s" % (w, timeout))
+        if conn.recv() != what:
+            raise RuntimeError("unexpected answer from SLSQP worker process %d" % w)
+
+    def put_values(self, ids, c):
+        self.arr["D"][np.asarray(ids, dtype=np.int64)] = c
+        self._vals = list(ids)
+
+    def put_normals(self, ids, J, G):
+        idx = np.asarray(ids, dtype=np.int64)
+        self.arr["J"][idx] = J
+        self._use_g = G is not None
+        if G is not None:
+            self.arr["G"][idx] = G
+        self._norms = list(ids)
+
+    def step(self, active):
+        W = self.W
+        for w, conn in enumerate(self.conns):
+            pick = lambda ids: [b for b in ids if b % W == w]
+            conn.send(("step", pick(self._vals), pick(self._norms), self._use_g, pick(active)))
+        for w in range(W):
+            self._wait(w, "done")
+        self._vals, self._norms = [], []
+
+    def x(self, b):
+        return self.arr["X"][b]
+
+    def mode(self, b):
+        return int(self.arr["mode"][b])
+
+    def iters(self, b):
+        return int(self.arr["iter"][b])
+
+    def fx(self, b):
+        return float(self.arr["fx"][b])
+
+    def close(self):
+        import shutil
+        for conn in self.conns:
+            try:
+                conn.send(("stop",))
+                conn.close()
+            except Exception:
+                pass
+        for pr in self.procs:
+            try:
+                pr.wait(timeout=10)
+            except Exception:
+                pr.kill()
+        self.arr = {}
+        for sh in self.shms.values():
+            try:
+                sh.close()
+                sh.unlink()
+            except Exception:
+                pass
+        self.shms, self.conns, self.procs = {}, [], []
+        shutil.rmtree(self._dir, ignore_errors=True)
+
+
 def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_grad=None,
-                threads=1, callback=None):
+                threads=1, callback=None, processes=0):
     """Run SLSQP on every row of X0 in lock step.
 
     evaluator : object with eval(X) and eval_fd(X) (see module docstring)
     lb, ub    : (n,) bounds with +-inf for "none" (SciPy clips x0 into them first)
     cost_grad : optional callable x -> (n,) user gradient of the cost (reference
                 `cost_derivative`, optimize.py:730-733); default = the FD row of J
-    threads   : host threads stepping the per-instance QP cores
+    threads   : host threads stepping the per-instance QP cores (SciPy's step holds the GIL: no gain)
+    processes : > 1: the per-instance SLSQP states live in that many worker processes and a lock-step
+                round steps them in parallel (shared-memory exchange); bitwise the result of a single
+                process running with one BLAS thread
     Returns dict(x (B, n), fun (B,), status (B,), nit (B,), nfev, njev, message list).
     """
-    slsqp, ilp64 = _low_level()
+    _low_level()
     X0 = np.atleast_2d(np.asarray(X0, dtype=np.float64))
     B, n = X0.shape
     m = int(meq + mineq)
@@ -86,65 +309,53 @@ def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_g
     X0 = np.clip(X0, lb, ub)                                 # _slsqp_py.py:322
     xl = np.where(np.isfinite(lb), lb, np.nan)               # the C core wants NaN for "no bound"
     xu = np.where(np.isfinite(ub), ub, np.nan)
-    inst = [_Instance(X0[b], n, m, int(meq), float(ftol), maxiter, np.int64 if ilp64 else np.int32)
-            for b in range(B)]
+    if processes and processes > 1 and B > 1:
+        st = _ProcessStepper(X0, n, m, int(meq), float(ftol), maxiter, xl, xu, processes)
+    else:
+        st = _LocalStepper(X0, n, m, int(meq), float(ftol), maxiter, xl, xu, threads)
+    nfev = np.zeros(B, dtype=int)
+    njev = np.zeros(B, dtype=int)
 
-    def put_values(ids, c):
-        for k, b in enumerate(ids):
-            it = inst[b]
-            it.fx = float(c[k, m])
-            it.d[:m] = c[k, :m]
-            it.nfev += 1
+    def grads(ids):
+        if cost_grad is None:
+            return None
+        return np.stack([np.asarray(cost_grad(np.array(st.x(b))), dtype=np.float64) for b in ids])
 
-    def put_normals(ids, J):
-        for k, b in enumerate(ids):
-            it = inst[b]
-            it.C[:m, :] = J[k, :, :m].T
-            it.g[:] = cost_grad(it.x) if cost_grad is not None else J[k, :, m]
-            it.njev += 1
-
-    # mode 0 on entry: objective, constraints and gradients at the start point
-    ids = list(range(B))
-    c, J = evaluator.eval_fd(np.stack([inst[b].x for b in ids]))
-    put_values(ids, c)
-    put_normals(ids, J)
-
-    def step(b):
-        it = inst[b]
-        slsqp(it.state, it.fx, it.g, it.C, it.d, it.x, it.mult, xl, xu, it.buffer, it.indices)
-        return b
-
-    active = list(range(B))
-    pool = ThreadPoolExecutor(threads) if threads > 1 else None
-    iters_prev = [0] * B
     try:
+        # mode 0 on entry: objective, constraints and gradients at the start point
+        ids = list(range(B))
+        c, J = evaluator.eval_fd(np.stack([st.x(b) for b in ids]))
+        st.put_values(ids, c)
+        st.put_normals(ids, J, grads(ids))
+        nfev += 1
+        njev += 1
+        active = list(range(B))
+        iters_prev = [0] * B
         while active:
-            if pool is not None:
-                list(pool.map(step, active))
-            else:
-                for b in active:
-                    step(b)
-            need_f = [b for b in active if inst[b].mode == 1]
-            need_g = [b for b in active if inst[b].mode == -1]
+            st.step(active)
+            need_f = [b for b in active if st.mode(b) == 1]
+            need_g = [b for b in active if st.mode(b) == -1]
             if need_f:
                 # SciPy clips x for the objective only (_clip_x_for_func); x stays inside the
                 # bounds in exact arithmetic, so the clip matters for 1-2 ulp excursions
-                Xf = np.stack([np.clip(inst[b].x, lb, ub) for b in need_f])
-                put_values(need_f, evaluator.eval(Xf))
+                Xf = np.stack([np.clip(st.x(b), lb, ub) for b in need_f])
+                st.put_values(need_f, evaluator.eval(Xf))
+                nfev[need_f] += 1
             if need_g:
-                Xg = np.stack([inst[b].x for b in need_g])
+                Xg = np.stack([st.x(b) for b in need_g])
                 _, Jg = evaluator.eval_fd(Xg)
-                put_normals(need_g, Jg)
+                st.put_normals(need_g, Jg, grads(need_g))
+                njev[need_g] += 1
             if callback is not None:
                 for b in active:
-                    if inst[b].state["iter"] > iters_prev[b]:
-                        callback(b, inst[b].x, inst[b].fx)
-                    iters_prev[b] = inst[b].state["iter"]
-            active = [b for b in active if abs(inst[b].mode) == 1]
+                    if st.iters(b) > iters_prev[b]:
+                        callback(b, np.array(st.x(b)), st.fx(b))
+                    iters_prev[b] = st.iters(b)
+            active = [b for b in active if abs(st.mode(b)) == 1]
+        modes = [st.mode(b) for b in range(B)]
+        return {"x": np.stack([np.array(st.x(b)) for b in range(B)]),
+                "fun": np.array([st.fx(b) for b in range(B)]),
+                "status": np.array(modes), "nit": np.array([st.iters(b) for b in range(B)]),
+                "nfev": nfev, "njev": njev, "message": [EXIT_MODES.get(k, "?") for k in modes]}
     finally:
-        if pool is not None:
-            pool.shutdown()
-    return {"x": np.stack([it.x for it in inst]), "fun": np.array([it.fx for it in inst]),
-            "status": np.array([it.mode for it in inst]), "nit": np.array([it.state["iter"] for it in inst]),
-            "nfev": np.array([it.nfev for it in inst]), "njev": np.array([it.njev for it in inst]),
-            "message": [EXIT_MODES.get(it.mode, "?") for it in inst]}
+        st.close()

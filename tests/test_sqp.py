@@ -109,3 +109,25 @@ def test_scipy_slsqp_needs_contiguous_gradient():
     if np.array_equal(good, bad):
         pytest.skip("this SciPy handles strided gradients")
     assert not np.array_equal(good, bad)
+
+
+def test_process_parallel_stepping_is_bitwise_identical():
+    """processes=2: the SLSQP states live in worker subprocesses (shared-memory exchange); same result
+    as one process with a single BLAS thread, same batched evaluator calls, with and without a user
+    cost gradient."""
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    meq, mineq = 64, 41
+    P = np.vstack([wl.prob.p[None], workloads.make_batch(wl, 4)])
+    grad = lambda x: wl.prob.eval_cost_derivative(x, wl.obj)
+    for cg in (None, grad):
+        ev1, ev2 = OracleEvaluator(wl), OracleEvaluator(wl)
+        seen = []
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(1):                  # the workers run SLSQP's LAPACK with one BLAS thread
+            one = sqp.slsqp_batch(ev1, P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5, cost_grad=cg)
+        two = sqp.slsqp_batch(ev2, P, ev2.lb, ev2.ub, meq, mineq, ftol=1e-6, maxiter=5, cost_grad=cg, processes=2,
+                              callback=lambda b, x, f: seen.append(b))
+        for key in ("x", "fun", "status", "nit", "nfev", "njev"):
+            assert np.array_equal(one[key], two[key]), key
+        assert one["message"] == two["message"] and ev1.calls == ev2.calls
+        assert set(seen) == set(range(len(P)))
