@@ -320,10 +320,15 @@ class Problem:
         self._engine = engine.DeviceProblem(ir, self.bounds_arrays(), device or self.device, jit=jit)
         return self._engine
 
-    def evaluate_batch(self, P, obj=None, jacobian=True):
+    def evaluate_batch(self, P, obj=None, jacobian=True, host=False):
         """Batched hot path: P (B, nvars) -> c (B, m+1) [, J (B, nvars, m+1)] as torch CUDA
-        tensors; row m carries cost / grad cost.  J[b, j, :] is column j."""
+        tensors; row m carries cost / grad cost.  J[b, j, :] is column j.  host=True: P is a host
+        array and the results come back as numpy arrays in host memory through the host-buffer
+        session (ogb_host_eval_fd: packed device->host transport, dense J rebuilt by host threads)."""
         eng = self._engine if self._engine is not None else self.compile(obj)
+        if host:
+            ev = eng.host_evaluator()
+            return ev.eval_fd(np.asarray(P, dtype=np.float64)) if jacobian else ev.eval(np.asarray(P, dtype=np.float64))
         return eng.eval_fd(P) if jacobian else eng.eval(P)
 
     def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None, processes=0):

@@ -265,3 +265,18 @@ def test_bound_adjusted_steps_vs_oracle(torch_cuda, api):
         assert_J_close(J[b].T, J_ref)
         checked += 1
     assert checked >= 5
+
+
+def test_solve_batch_with_worker_processes(torch_cuda, api, capsys):
+    """Device evaluations + SLSQP cores in worker subprocesses == the in-process driver (one BLAS thread)."""
+    from threadpoolctl import threadpool_limits
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    P0 = np.vstack([np.array(wl.prob.p)[None], workloads.make_batch(wl, 4)])
+    with threadpool_limits(1):
+        one = wl.prob.solve_batch(P0, wl.obj, ftol=1e-6, maxiter=25, max_outer=2)
+    two = wl.prob.solve_batch(P0, wl.obj, ftol=1e-6, maxiter=25, max_outer=2, processes=2)
+    capsys.readouterr()
+    for key in ("x", "fun", "status", "nit", "outer"):
+        assert np.array_equal(one[key], two[key]), key
+    assert (two["status"] == 0).all()

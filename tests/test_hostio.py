@@ -129,3 +129,15 @@ def test_host_session_full_size_roundtrip(api):
     Jt = torch.from_numpy(J).to(J_d.device)
     assert bool((Jt == J_d).all()) and (c == c_d.cpu().numpy()).all()
     S.close()
+
+
+@pytest.mark.gpu
+def test_facade_evaluate_batch_host(api):
+    import torch
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg3_goddard_knot30x2", api)
+    P = workloads.make_batch(wl, 9)
+    c_d, J_d = wl.prob.evaluate_batch(P, wl.obj)
+    c_h, J_h = wl.prob.evaluate_batch(P, wl.obj, host=True)
+    assert isinstance(c_h, np.ndarray) and (c_h == c_d.cpu().numpy()).all() and (J_h == J_d.cpu().numpy()).all()
+    assert (wl.prob.evaluate_batch(P, wl.obj, jacobian=False, host=True) == c_h).all()
