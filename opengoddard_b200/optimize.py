@@ -369,17 +369,23 @@ class Problem:
             def grad(x):
                 self.p = x
                 return np.ascontiguousarray(self.cost_derivative(self, obj), dtype=np.float64)
-        for _ in range(self.maxIterator if max_outer is None else max_outer):
-            ids = np.nonzero(status != 0)[0]
-            if ids.size == 0:
-                break
-            res = sqp.slsqp_batch(eng.host_evaluator(), X[ids], lb, ub, eng.meq, eng.mineq, ftol=ftol,
-                                  maxiter=maxiter, cost_grad=grad, threads=threads, processes=processes)
-            X[ids] = res["x"]
-            status[ids] = res["status"]
-            fun[ids] = res["fun"]
-            nit[ids] += res["nit"]
-            outer[ids] += 1
+        pool = sqp.WorkerPool(min(int(processes), B)) if processes and processes > 1 and B > 1 else None
+        try:                                                # one set of worker processes for all outer passes
+            for _ in range(self.maxIterator if max_outer is None else max_outer):
+                ids = np.nonzero(status != 0)[0]
+                if ids.size == 0:
+                    break
+                res = sqp.slsqp_batch(eng.host_evaluator(), X[ids], lb, ub, eng.meq, eng.mineq, ftol=ftol,
+                                      maxiter=maxiter, cost_grad=grad, threads=threads,
+                                      processes=pool if pool is not None else 0)
+                X[ids] = res["x"]
+                status[ids] = res["status"]
+                fun[ids] = res["fun"]
+                nit[ids] += res["nit"]
+                outer[ids] += 1
+        finally:
+            if pool is not None:
+                pool.close()
         return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
 
     # ------------------------------------------------------------------ solve (:649-755)

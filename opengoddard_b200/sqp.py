@@ -119,27 +119,46 @@ class _LocalStepper:
 
 
 def _worker_loop(conn):
-    """Body of a worker process of _ProcessStepper (entry point: python -m opengoddard_b200.sqp_worker):
-    owns the SLSQP state of its instances; X, c, J, G, mode and iteration counters live in shared
-    memory created by the parent."""
+    """Body of a worker process (entry point: python -m opengoddard_b200.sqp_worker).  Serves any
+    number of batched solves: every ("init", ...) message attaches the parent's shared memory and
+    builds the SLSQP states of the instances this worker owns; ("step", ...) messages advance them."""
     from multiprocessing import shared_memory
     slsqp, ilp64 = _low_level()
-    names, shapes, owned, n, m, meq, acc, maxiter, xl, xu = conn.recv()
-    shms = {k: shared_memory.SharedMemory(name=v) for k, v in names.items()}
-    try:                                   # the parent owns (and unlinks) the segments: attaching must not
-        from multiprocessing import resource_tracker     # register them with this process' tracker (< 3.13)
+    shms, arr, inst = {}, {}, {}
+
+    def release():
+        arr.clear()
+        inst.clear()
         for sh in shms.values():
-            resource_tracker.unregister(sh._name, "shared_memory")
-    except Exception:
-        pass
-    arr = {k: np.ndarray(shapes[k][0], dtype=shapes[k][1], buffer=shms[k].buf) for k in names}
-    inst = {b: _Instance(arr["X"][b], n, m, meq, acc, maxiter, np.int64 if ilp64 else np.int32) for b in owned}
-    conn.send("ready")
+            sh.close()
+        shms.clear()
+
     try:
         while True:
             msg = conn.recv()
             if msg[0] == "stop":
                 break
+            if msg[0] == "init":
+                release()
+                _, names, shapes, owned, n, m, meq, acc, maxiter, xl, xu = msg
+                for k, v in names.items():
+                    shms[k] = shared_memory.SharedMemory(name=v)
+                try:                               # the parent owns (and unlinks) the segments: attaching must
+                    from multiprocessing import resource_tracker     # not register them with this tracker (< 3.13)
+                    for sh in shms.values():
+                        resource_tracker.unregister(sh._name, "shared_memory")
+                except Exception:
+                    pass
+                for k in names:
+                    arr[k] = np.ndarray(shapes[k][0], dtype=shapes[k][1], buffer=shms[k].buf)
+                for b in owned:
+                    inst[b] = _Instance(arr["X"][b], n, m, meq, acc, maxiter, np.int64 if ilp64 else np.int32)
+                conn.send("ready")
+                continue
+            if msg[0] == "release":
+                release()
+                conn.send("released")
+                continue
             _, vals, norms, use_g, active = msg
             for b in vals:
                 it = inst[b]
@@ -158,43 +177,27 @@ def _worker_loop(conn):
                 arr["fx"][b] = it.fx
             conn.send("done")
     finally:
-        del arr, inst
-        for sh in shms.values():
-            sh.close()
+        release()
 
 
-class _ProcessStepper:
-    """The SLSQP states are spread over worker PROCESSES (instance b belongs to worker b mod W), so
-    the QP cores of a lock-step round run in parallel on the host cores; decision vectors,
-    constraint values and Jacobians are exchanged through shared memory.  Same arithmetic per
-    instance as _LocalStepper (the instances are independent).  The workers are plain
-    `python -m opengoddard_b200.sqp_worker` subprocesses connected over a local socket -- not
-    multiprocessing children -- so an unguarded user script (the reference's examples have no
-    `if __name__ == "__main__"`) is never re-executed and no CUDA context is forked."""
+class WorkerPool:
+    """Worker processes for the SLSQP cores, reusable across slsqp_batch calls (Problem.solve_batch keeps
+    one for all its outer passes).  The workers are plain `python -m opengoddard_b200.sqp_worker`
+    subprocesses connected over a local socket -- not multiprocessing children -- so an unguarded
+    user script (the reference's examples have no `if __name__ == "__main__"`) is never re-executed
+    and no CUDA context is forked.  Each worker runs SLSQP's LAPACK with one BLAS thread."""
 
-    def __init__(self, X0, n, m, meq, acc, maxiter, xl, xu, processes):
+    def __init__(self, processes):
         import os
         import secrets
         import subprocess
         import sys
         import tempfile
-        from multiprocessing import connection, shared_memory
-        B = len(X0)
-        self.m, self.B, self.W = m, B, max(1, min(int(processes), B))
-        shapes = {"X": ((B, n), np.float64), "D": ((B, m + 1), np.float64), "J": ((B, n, m + 1), np.float64),
-                  "G": ((B, n), np.float64), "mode": ((B,), np.int64), "iter": ((B,), np.int64),
-                  "fx": ((B,), np.float64)}
-        self.shms, self.arr, self.conns, self.procs = {}, {}, [], []
-        self._vals, self._norms, self._use_g = [], [], False
+        from multiprocessing import connection
+        self.W = max(1, int(processes))
+        self.conns, self.procs = [], []
         self._dir = tempfile.mkdtemp(prefix="ogb200_sqp_")
         try:
-            for k, (shape, dt) in shapes.items():
-                nbytes = max(8, int(np.prod(shape)) * np.dtype(dt).itemsize)
-                self.shms[k] = shared_memory.SharedMemory(create=True, size=nbytes)
-                self.arr[k] = np.ndarray(shape, dtype=dt, buffer=self.shms[k].buf)
-                self.arr[k][...] = 0
-            self.arr["X"][...] = X0
-            names = {k: v.name for k, v in self.shms.items()}
             key = secrets.token_bytes(16)
             address = os.path.join(self._dir, "sock")
             root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -209,16 +212,12 @@ class _ProcessStepper:
                                                        env=env, stdin=subprocess.DEVNULL))
                 listener._listener._socket.settimeout(120.0)
                 for w in range(self.W):
-                    conn = listener.accept()
-                    conn.send((names, shapes, list(range(w, B, self.W)), n, m, meq, acc, maxiter, xl, xu))
-                    self.conns.append(conn)
-            for w in range(self.W):
-                self._wait(w, "ready")
+                    self.conns.append(listener.accept())
         except Exception:
             self.close()
             raise
 
-    def _wait(self, w, what, timeout=600.0):
+    def wait(self, w, what, timeout=600.0):
         conn, waited = self.conns[w], 0.0
         while not conn.poll(0.5):
             waited += 0.5
@@ -228,6 +227,61 @@ class _ProcessStepper:
                 raise RuntimeError("SLSQP worker process %d did not answer within %g s" % (w, timeout))
         if conn.recv() != what:
             raise RuntimeError("unexpected answer from SLSQP worker process %d" % w)
+
+    def close(self):
+        import shutil
+        for conn in self.conns:
+            try:
+                conn.send(("stop",))
+                conn.close()
+            except Exception:
+                pass
+        for pr in self.procs:
+            try:
+                pr.wait(timeout=10)
+            except Exception:
+                pr.kill()
+        self.conns, self.procs = [], []
+        shutil.rmtree(self._dir, ignore_errors=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class _ProcessStepper:
+    """The SLSQP states are spread over the processes of a WorkerPool (instance b belongs to worker
+    b mod W), so the QP cores of a lock-step round run in parallel on the host cores; decision vectors,
+    constraint values and Jacobians are exchanged through shared memory.  Same arithmetic per
+    instance as _LocalStepper (the instances are independent)."""
+
+    def __init__(self, X0, n, m, meq, acc, maxiter, xl, xu, pool, own_pool):
+        from multiprocessing import shared_memory
+        B = len(X0)
+        self.m, self.B, self.pool, self.own_pool = m, B, pool, own_pool
+        self.W = min(pool.W, B)
+        shapes = {"X": ((B, n), np.float64), "D": ((B, m + 1), np.float64), "J": ((B, n, m + 1), np.float64),
+                  "G": ((B, n), np.float64), "mode": ((B,), np.int64), "iter": ((B,), np.int64),
+                  "fx": ((B,), np.float64)}
+        self.shms, self.arr = {}, {}
+        self._vals, self._norms, self._use_g = [], [], False
+        try:
+            for k, (shape, dt) in shapes.items():
+                nbytes = max(8, int(np.prod(shape)) * np.dtype(dt).itemsize)
+                self.shms[k] = shared_memory.SharedMemory(create=True, size=nbytes)
+                self.arr[k] = np.ndarray(shape, dtype=dt, buffer=self.shms[k].buf)
+                self.arr[k][...] = 0
+            self.arr["X"][...] = X0
+            names = {k: v.name for k, v in self.shms.items()}
+            for w in range(self.W):
+                pool.conns[w].send(("init", names, shapes, list(range(w, B, self.W)), n, m, meq, acc, maxiter, xl, xu))
+            for w in range(self.W):
+                pool.wait(w, "ready")
+        except Exception:
+            self.close()
+            raise
 
     def put_values(self, ids, c):
         self.arr["D"][np.asarray(ids, dtype=np.int64)] = c
@@ -243,11 +297,11 @@ class _ProcessStepper:
 
     def step(self, active):
         W = self.W
-        for w, conn in enumerate(self.conns):
-            pick = lambda ids: [b for b in ids if b % W == w]
-            conn.send(("step", pick(self._vals), pick(self._norms), self._use_g, pick(active)))
         for w in range(W):
-            self._wait(w, "done")
+            pick = lambda ids: [b for b in ids if b % W == w]
+            self.pool.conns[w].send(("step", pick(self._vals), pick(self._norms), self._use_g, pick(active)))
+        for w in range(W):
+            self.pool.wait(w, "done")
         self._vals, self._norms = [], []
 
     def x(self, b):
@@ -263,18 +317,16 @@ class _ProcessStepper:
         return float(self.arr["fx"][b])
 
     def close(self):
-        import shutil
-        for conn in self.conns:
-            try:
-                conn.send(("stop",))
-                conn.close()
-            except Exception:
-                pass
-        for pr in self.procs:
-            try:
-                pr.wait(timeout=10)
-            except Exception:
-                pr.kill()
+        try:
+            if self.pool.conns and not self.own_pool:      # detach the workers before the segments go away
+                for w in range(self.W):
+                    self.pool.conns[w].send(("release",))
+                for w in range(self.W):
+                    self.pool.wait(w, "released", timeout=30.0)
+        except Exception:
+            pass
+        if self.own_pool:
+            self.pool.close()
         self.arr = {}
         for sh in self.shms.values():
             try:
@@ -282,8 +334,7 @@ class _ProcessStepper:
                 sh.unlink()
             except Exception:
                 pass
-        self.shms, self.conns, self.procs = {}, [], []
-        shutil.rmtree(self._dir, ignore_errors=True)
+        self.shms = {}
 
 
 def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_grad=None,
@@ -295,7 +346,8 @@ def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_g
     cost_grad : optional callable x -> (n,) user gradient of the cost (reference
                 `cost_derivative`, optimize.py:730-733); default = the FD row of J
     threads   : host threads stepping the per-instance QP cores (SciPy's step holds the GIL: no gain)
-    processes : > 1: the per-instance SLSQP states live in that many worker processes and a lock-step
+    processes : > 1 (or a WorkerPool to reuse): the per-instance SLSQP states live in that many worker
+                processes and a lock-step
                 round steps them in parallel (shared-memory exchange); bitwise the result of a single
                 process running with one BLAS thread
     Returns dict(x (B, n), fun (B,), status (B,), nit (B,), nfev, njev, message list).
@@ -309,8 +361,10 @@ def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_g
     X0 = np.clip(X0, lb, ub)                                 # _slsqp_py.py:322
     xl = np.where(np.isfinite(lb), lb, np.nan)               # the C core wants NaN for "no bound"
     xu = np.where(np.isfinite(ub), ub, np.nan)
-    if processes and processes > 1 and B > 1:
-        st = _ProcessStepper(X0, n, m, int(meq), float(ftol), maxiter, xl, xu, processes)
+    if isinstance(processes, WorkerPool) and B >= 1:     # (also a batch of one: same BLAS threading as the rest)
+        st = _ProcessStepper(X0, n, m, int(meq), float(ftol), maxiter, xl, xu, processes, False)
+    elif not isinstance(processes, WorkerPool) and processes and processes > 1 and B > 1:
+        st = _ProcessStepper(X0, n, m, int(meq), float(ftol), maxiter, xl, xu, WorkerPool(min(int(processes), B)), True)
     else:
         st = _LocalStepper(X0, n, m, int(meq), float(ftol), maxiter, xl, xu, threads)
     nfev = np.zeros(B, dtype=int)

@@ -131,3 +131,20 @@ def test_process_parallel_stepping_is_bitwise_identical():
             assert np.array_equal(one[key], two[key]), key
         assert one["message"] == two["message"] and ev1.calls == ev2.calls
         assert set(seen) == set(range(len(P)))
+
+
+def test_worker_pool_is_reusable_across_solves():
+    """One WorkerPool serves several slsqp_batch calls (different batch sizes), like solve_batch's passes."""
+    from threadpoolctl import threadpool_limits
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    meq, mineq = 64, 41
+    P = workloads.make_batch(wl, 5)
+    with sqp.WorkerPool(3) as pool:
+        for rows in (P, P[:2], P[1:2]):
+            ev1, ev2 = OracleEvaluator(wl), OracleEvaluator(wl)
+            with threadpool_limits(1):
+                one = sqp.slsqp_batch(ev1, rows, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=3)
+            two = sqp.slsqp_batch(ev2, rows, ev2.lb, ev2.ub, meq, mineq, ftol=1e-6, maxiter=3, processes=pool)
+            assert np.array_equal(one["x"], two["x"]) and np.array_equal(one["status"], two["status"])
+        assert all(pr.poll() is None for pr in pool.procs)       # still alive between calls
+    assert pool.procs == []
