@@ -55,44 +55,59 @@ int host_isa() {
 }
 
 // ---------------------------------------------------------------- dense expansion of one instance
-constexpr int kPiece = 512;                      // doubles per L1-resident piece (4 KB)
+// dst[0, nM) = 0 except dst[lin[e]] = vals[e]; lin ascending.  The body is written one 64-byte line
+// at a time with non-temporal stores (no read-for-ownership): runs of all-zero lines (~90 % of a
+// Jacobian) come straight from a zero register, a line that holds values is assembled in a
+// register-sized scratch first.  isa: 1 = AVX2 (32-byte stores), 0 = SSE2, 2 = AVX-512.
+__attribute__((target("avx2"))) size_t zero_lines_avx2(double* dst, size_t pos, size_t stop) {
+    const __m256d z = _mm256_setzero_pd();
+    for (; pos + 8 <= stop; pos += 8) { _mm256_stream_pd(dst + pos, z); _mm256_stream_pd(dst + pos + 4, z); }
+    return pos;
+}
+__attribute__((target("avx2"))) void put_line_avx2(double* dst, const double* line) {
+    _mm256_stream_pd(dst, _mm256_load_pd(line));
+    _mm256_stream_pd(dst + 4, _mm256_load_pd(line + 4));
+}
+__attribute__((target("avx512f"))) size_t zero_lines_avx512(double* dst, size_t pos, size_t stop) {
+    const __m512d z = _mm512_setzero_pd();
+    for (; pos + 8 <= stop; pos += 8) _mm512_stream_pd(dst + pos, z);
+    return pos;
+}
+__attribute__((target("avx512f"))) void put_line_avx512(double* dst, const double* line) {
+    _mm512_stream_pd(dst, _mm512_load_pd(line));
+}
+size_t zero_lines_sse2(double* dst, size_t pos, size_t stop) {
+    const __m128d z = _mm_setzero_pd();
+    for (; pos + 8 <= stop; pos += 8)
+        for (int k = 0; k < 8; k += 2) _mm_stream_pd(dst + pos + k, z);
+    return pos;
+}
+void put_line_sse2(double* dst, const double* line) {
+    for (int k = 0; k < 8; k += 2) _mm_stream_pd(dst + k, _mm_load_pd(line + k));
+}
 
-__attribute__((target("avx2"))) void stream_piece_avx2(double* dst, const double* buf) {
-    for (int k = 0; k < kPiece; k += 8) {
-        _mm256_stream_pd(dst + k, _mm256_load_pd(buf + k));
-        _mm256_stream_pd(dst + k + 4, _mm256_load_pd(buf + k + 4));
-    }
-}
-__attribute__((target("avx512f"))) void stream_piece_avx512(double* dst, const double* buf) {
-    for (int k = 0; k < kPiece; k += 16) {
-        _mm512_stream_pd(dst + k, _mm512_load_pd(buf + k));
-        _mm512_stream_pd(dst + k + 8, _mm512_load_pd(buf + k + 8));
-    }
-}
-void stream_piece_sse2(double* dst, const double* buf) {
-    for (int k = 0; k < kPiece; k += 2) _mm_stream_pd(dst + k, _mm_load_pd(buf + k));
-}
-
-// dst[0, nM) = 0 except dst[lin[e]] = vals[e]; lin ascending.  The body is produced piece by
-// piece in an L1 buffer and streamed out with non-temporal stores (no read-for-ownership).
-// isa: 2 = AVX-512, 1 = AVX2, 0 = SSE2 non-temporal stores
 void expand_dense(double* dst, size_t nM, const double* vals, const uint32_t* lin, int nnz, int isa) {
-    alignas(64) double buf[kPiece];
     size_t pos = 0;
     int e = 0;
     size_t head = ((64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63) / sizeof(double);
     if (head > nM) head = nM;
     for (; pos < head; ++pos) dst[pos] = (e < nnz && lin[e] == pos) ? vals[e++] : 0.0;
-    std::memset(buf, 0, sizeof buf);
-    while (pos + kPiece <= nM) {
-        const int e0 = e;
-        const size_t end = pos + kPiece;
-        while (e < nnz && lin[e] < end) { buf[lin[e] - pos] = vals[e]; ++e; }
-        if (isa == 2) stream_piece_avx512(dst + pos, buf);
-        else if (isa == 1) stream_piece_avx2(dst + pos, buf);
-        else stream_piece_sse2(dst + pos, buf);
-        for (int q = e0; q < e; ++q) buf[lin[q] - pos] = 0.0;       // re-zero only what was touched
-        pos = end;
+    const size_t body_end = head + ((nM - head) & ~(size_t)7);       // whole 64-byte lines: [head, body_end)
+    alignas(64) double line[8];
+    while (pos < body_end) {
+        // all-zero lines up to the line that holds the next value (or to the end of the body)
+        size_t stop = body_end;
+        if (e < nnz && lin[e] < body_end) stop = head + ((lin[e] - head) & ~(size_t)7);
+        if (pos < stop)
+            pos = isa == 1 ? zero_lines_avx2(dst, pos, stop) : isa == 2 ? zero_lines_avx512(dst, pos, stop)
+                                                                        : zero_lines_sse2(dst, pos, stop);
+        if (pos >= body_end) break;
+        for (int k = 0; k < 8; ++k) line[k] = 0.0;                  // a line with values
+        while (e < nnz && lin[e] < pos + 8) { line[lin[e] - pos] = vals[e]; ++e; }
+        if (isa == 1) put_line_avx2(dst + pos, line);
+        else if (isa == 2) put_line_avx512(dst + pos, line);
+        else put_line_sse2(dst + pos, line);
+        pos += 8;
     }
     for (; pos < nM; ++pos) dst[pos] = (e < nnz && lin[e] == pos) ? vals[e++] : 0.0;
     _mm_sfence();
