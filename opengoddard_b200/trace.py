@@ -175,6 +175,23 @@ class TraceContext:
         self._table_ids[key] = len(self.tables) - 1
         return self._table_ids[key]
 
+    def table_of_arrays(self, xp, fp, left, right):
+        """Register the table of a numpy.interp(x, xp, fp, left, right) call; returns its table id.
+        numpy.interp is the formula ogb_interp calls variant 0 (compiled_base.c arr_interp), with
+        `left` / `right` (default fp[0] / fp[-1]) outside the table."""
+        xp = np.asarray(xp, dtype=float)
+        fp = np.asarray(fp, dtype=float)
+        if xp.ndim != 1 or fp.shape != xp.shape or len(xp) < 2 or not (np.diff(xp) >= 0).all():
+            raise TraceError("numpy.interp on traced values needs 1-D ascending xp and fp of equal length >= 2")
+        below = float(fp[0]) if left is None else float(left)
+        above = float(fp[-1]) if right is None else float(right)
+        key = ("np.interp", xp.tobytes(), fp.tobytes(), below, above)
+        if key not in self._table_ids:
+            self.tables.append(dict(x=xp.copy(), y=fp.copy(), variant=0, extrapolate=False,
+                                    fill_below=below, fill_above=above, keep=None))
+            self._table_ids[key] = len(self.tables) - 1
+        return self._table_ids[key]
+
     def section_of(self, g):
         for s in range(self.nsec - 1, -1, -1):
             if g >= self.g0[s]:
@@ -318,6 +335,12 @@ class Sym:
             return Sym(self.ctx, vec.rng, {s: g.op(name, a.parts, p) for s, p in vec.parts.items()})
         return Sym(self.ctx, vec.rng, {s: g.op(name, p, b.parts) for s, p in vec.parts.items()})
 
+    def _interp_table(self, tid):
+        g = self.ctx.graph
+        if self.rng is None:
+            return Sym(self.ctx, None, g.interp(tid, self.parts))
+        return Sym(self.ctx, self.rng, {s: g.interp(tid, p) for s, p in self.parts.items()})
+
     def _interp(self, f):
         """this value pushed through the scipy interp1d object `f`"""
         g, tid = self.ctx.graph, self.ctx.table_of(f)
@@ -420,6 +443,16 @@ def _apply_ufunc(name, inputs):
     if name == "power":
         a, b = inputs
         return a.__pow__(b) if isinstance(a, Sym) else b.__rpow__(a)
+    if name == "float_power":
+        a, b = inputs
+        return a.__pow__(b) if isinstance(a, Sym) else b.__rpow__(a)
+    if name == "hypot":                       # sqrt(a^2 + b^2): within an ulp of libm's hypot
+        a, b = inputs
+        return _apply_ufunc("sqrt", (a * a + b * b,))
+    if name == "exp2":
+        return inputs[0].__rpow__(2.0)
+    if name == "log2":
+        return _apply_ufunc("log", (inputs[0],)) / float(np.log(2.0))
     if name == "deg2rad" or name == "radians":
         return inputs[0] * (np.pi / 180.0)
     if name == "rad2deg" or name == "degrees":
@@ -446,6 +479,27 @@ def _apply_function(func, args, kwargs):
         secs = next(x.parts for x in (cond, a, b) if x.rng is not None).keys()
         pick = lambda x, s: x.parts if x.rng is None else x.parts[s]
         return Sym(ctx, rng, {s: g.op("sel", pick(cond, s), pick(a, s), pick(b, s)) for s in secs})
+    if name == "clip" and len(args) + len(kwargs) >= 2 and is_sym(args[0]):
+        lo = args[1] if len(args) > 1 else kwargs.get("a_min", kwargs.get("min"))
+        hi = args[2] if len(args) > 2 else kwargs.get("a_max", kwargs.get("max"))
+        out = args[0]
+        if lo is not None:
+            out = np.maximum(out, lo)
+        if hi is not None:
+            out = np.minimum(out, hi)
+        return out
+    if name == "interp" and len(args) >= 3 and is_sym(args[0]) and not is_sym(args[1]) and not is_sym(args[2]):
+        if kwargs.get("period") is not None:
+            raise TraceError("numpy.interp(period=...) is not supported on traced values")
+        x = args[0]
+        ctx = x.ctx
+        tid = ctx.table_of_arrays(args[1], args[2], kwargs.get("left", args[3] if len(args) > 3 else None),
+                                  kwargs.get("right", args[4] if len(args) > 4 else None))
+        if isinstance(x, SymList):
+            return SymList([e._interp_table(tid) if isinstance(e, Sym) else
+                            float(np.interp(e, args[1], args[2], left=ctx.tables[tid]["fill_below"],
+                                            right=ctx.tables[tid]["fill_above"])) for e in x.items])
+        return x._interp_table(tid)
     if name in ("hstack", "concatenate") and len(args) >= 1:
         seq = list(args[0])
         out = []

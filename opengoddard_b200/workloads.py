@@ -846,11 +846,14 @@ CONFIGS["edge_table_lookup"] = (table_lookup, (12, 9))
 def all_ops(api, nodes=(9, 6)):
     """Edge case: every numpy ufunc / operator the tracer accepts that no other workload uses
     (tan, arcsin, arccos, arctan, sinh, log, log10, sign, floor, ceil, square, reciprocal, fabs,
-    minimum, maximum, fmin, fmax, non-integer and negative powers, scalar ** array, comparisons,
-    logical_and / or / not, unary minus / plus, deg2rad) in dynamics, point rows, scalar rows, the
+    minimum, maximum, fmin, fmax, clip, hypot, exp2, log2, float_power, numpy.interp tables, non-integer
+    and negative powers, scalar ** array, comparisons, logical_and / or / not, unary minus / plus,
+    deg2rad) in dynamics, point rows, scalar rows, the
     cost and a running cost -- smooth arguments only, so the forward differences are well defined."""
     class Par:
         a, b = 0.8, 1.7
+        tab_x = np.array([0.5, 1.0, 1.6, 2.2, 2.4, 3.5])
+        tab_y = np.array([0.1, 0.7, 0.4, 0.9, 1.5, 1.1])
 
     par = Par()
     prob = api.Problem([0.0, 2.0, 3.0], list(nodes), [3, 3], [2, 2], 3)
@@ -865,7 +868,10 @@ def all_ops(api, nodes=(9, 6)):
         u = prob.controls(0, section)
         w = prob.controls(1, section)
         d = api.Dynamics(prob, section)
-        d[0] = np.tan(0.5 * x) + np.arcsin(z) * np.arccos(0.5 * z) - np.sinh(z) + np.log(y) * np.log10(1.0 + y)
+        d[0] = (np.tan(0.5 * x) + np.arcsin(z) * np.arccos(0.5 * z) - np.sinh(z) + np.log(y) * np.log10(1.0 + y)
+                + np.clip(u, -0.1, 0.45) * np.hypot(x, y) + np.exp2(z) * np.log2(y)
+                + np.interp(y, obj.tab_x, obj.tab_y) - np.interp(z, obj.tab_x - 2.0, obj.tab_y, left=-1.0, right=4.0)
+                + np.float_power(y, 1.25) + np.clip(w, None, 0.2))
         d[1] = (np.minimum(u, 0.3 * y) + np.maximum(w, -x) + np.fmin(x, 0.95) * np.fmax(z, -0.9)
                 + np.square(x) * np.reciprocal(y) + np.fabs(z - 2.0) + y ** 0.5 + y ** -1.5 + 2.0 ** x
                 + np.power(y, obj.a))
