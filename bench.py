@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-variants", action="store_true")
+    ap.add_argument("--autotune", action="store_true", help="let the engine pick the sweep kernel's CTA size (256 / 384) first")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads of the e2e session (default: cores / ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -271,6 +272,9 @@ def main():
     wl = workloads.build(cfg, api)
     eng = wl.prob.compile(wl.obj, device=dev)
     B = args.batch
+    tuned = None
+    if args.autotune:                                   # set-up, before anything is timed
+        tuned = eng.autotune(workloads.make_batch(wl, min(B, 512), first=rank * B))
     # this rank's shard of the seeded global batch (instances rank*B .. rank*B + B - 1)
     P_host = torch.from_numpy(workloads.make_batch(wl, B, first=rank * B)).pin_memory()
     P = P_host.to(dev)
@@ -423,7 +427,9 @@ def main():
                        "rows": M, "meq": eng.meq, "mineq": eng.mineq, "bytes_per_eval": bytes_per_eval,
                        "l2": "256 MiB memset between timed steps (outside the event pairs); every step "
                              "also writes %.2f GB of Jacobian (L2 is 126 MB)" % (B * bytes_per_eval / 1e9),
-                       "parallelism": "instance batch sharded over %d GPU(s), no data-path collective" % world},
+                       "parallelism": "instance batch sharded over %d GPU(s), no data-path collective" % world,
+                       "sweep_cta_threads": int(getattr(eng, "tuned_threads", 256)),
+                       "autotune_ms": tuned},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches, "gpu_launches_per_e2e_step": launches_e2e,

@@ -152,7 +152,8 @@ int   ogb_problem_info_get(void* prob, ogb_problem_info* out);
 enum ogb_option {
     OGB_OPT_GENERIC_COLUMNS = 0, /* 1: produce Jacobian columns with the generic per-row code instead of
                                     the register-cached fast path (results must be bit-identical)     */
-    OGB_OPT_THREADS = 1,         /* CTA size of the sweep kernel: 64, 128, 192 or 256         */
+    OGB_OPT_THREADS = 1,         /* CTA size of the sweep kernel: a multiple of 32 up to 256 (up to 512 for the
+                                    NVRTC-specialised kernel only); DeviceProblem.autotune tries 256 and 384  */
     OGB_OPT_JIT = 2,             /* 1: run the NVRTC-specialised sweep kernel (tapes compiled to device
                                     code), 0: the ahead-of-time kernel with the tape interpreter       */
     OGB_OPT_GRID_CAP = 3,        /* cap on the persistent grid (0 = SM count x resident CTAs)         */

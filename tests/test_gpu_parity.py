@@ -280,3 +280,22 @@ def test_solve_batch_with_worker_processes(torch_cuda, api, capsys):
     for key in ("x", "fun", "status", "nit", "outer"):
         assert np.array_equal(one[key], two[key]), key
     assert (two["nit"] > 0).all()
+
+
+def test_autotune_keeps_results_bit_identical(torch_cuda, api):
+    """DeviceProblem.autotune times the 256- and 384-thread builds of the sweep kernel and keeps one;
+    c and J do not depend on the choice."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg4_polar3x40", api)
+    eng = wl.prob.compile(wl.obj)
+    P = workloads.make_batch(wl, 24)
+    c0, J0 = eng.eval_fd(P)
+    timings = eng.autotune(P, min_gain=0.0)
+    assert set(timings) == {256, 384} and eng.tuned_threads in timings
+    c1, J1 = eng.eval_fd(P)
+    assert torch_cuda.equal(c0, c1) and torch_cuda.equal(J0, J1)
+    for thr in (384, 256):
+        eng.set_option(1, thr)
+        c2, J2 = eng.eval_fd(P)
+        assert torch_cuda.equal(c0, c2) and torch_cuda.equal(J0, J2)
+        assert torch_cuda.equal(eng.eval(P), c0)
