@@ -47,8 +47,10 @@ J_DUST = 1e-7          # zero-pattern exceptions: a forward difference of two va
 #                        CUDA's and glibc's exp/sin/cos round differently in the last place
 
 
-def assert_J_close(J, J_ref):
-    """J, J_ref: (..., M, n).  Row-scaled tolerance + identical zero pattern (up to FD dust)."""
+def assert_J_close(J, J_ref, dust=None):
+    """J, J_ref: (..., M, n).  Row-scaled tolerance + identical zero pattern (up to FD dust:
+    J_DUST * rowmax unless `dust` widens it, never beyond the value tolerance J_RTOL)."""
+    dust = J_DUST if dust is None else min(float(dust), J_RTOL)
     J, J_ref = np.asarray(J), np.asarray(J_ref)
     assert J.shape == J_ref.shape
     rowmax = np.abs(J_ref).max(axis=-1, keepdims=True)
@@ -58,7 +60,7 @@ def assert_J_close(J, J_ref):
         err / np.maximum(rowmax, 1e-300)).max()
     mism = (J == 0) != (J_ref == 0)
     if mism.any():
-        big = np.maximum(np.abs(J), np.abs(J_ref)) > J_DUST * rowmax
+        big = np.maximum(np.abs(J), np.abs(J_ref)) > dust * rowmax
         assert not (mism & big).any(), "Jacobian zero pattern differs in %d entries (largest %g of rowmax)" % (
             (mism & big).sum(), (np.maximum(np.abs(J), np.abs(J_ref)) / np.maximum(rowmax, 1e-300))[mism].max())
         assert mism.sum() <= max(2, J.size // 100000), "too many dust-level zero-pattern differences: %d" % mism.sum()
