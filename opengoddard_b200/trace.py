@@ -443,6 +443,23 @@ def _apply_ufunc(name, inputs):
     if name == "power":
         a, b = inputs
         return a.__pow__(b) if isinstance(a, Sym) else b.__rpow__(a)
+    if name == "expm1":                       # exp(x) - 1 (absolute error ~1e-16: enough for an FD Jacobian)
+        return _apply_ufunc("exp", (inputs[0],)) - 1.0
+    if name == "log1p":
+        return _apply_ufunc("log", (inputs[0] + 1.0,))
+    if name == "isnan":
+        return _apply_ufunc("not_equal", (inputs[0], inputs[0]))
+    if name in ("remainder", "mod"):          # sign of the divisor, like numpy: x - floor(x / y) * y
+        a, b = inputs
+        return a - _apply_ufunc("floor", (a / b,)) * b
+    if name == "fmod":                        # sign of the dividend, like C: x - trunc(x / y) * y
+        a, b = inputs
+        q = a / b
+        tr = _apply_function(np.where, (q < 0.0, _apply_ufunc("ceil", (q,)), _apply_ufunc("floor", (q,))), {})
+        return a - tr * b
+    if name == "heaviside":
+        x, h0 = inputs
+        return _apply_function(np.where, (x < 0.0, 0.0, _apply_function(np.where, (x > 0.0, 1.0, h0), {})), {})
     if name == "float_power":
         a, b = inputs
         return a.__pow__(b) if isinstance(a, Sym) else b.__rpow__(a)
@@ -479,6 +496,39 @@ def _apply_function(func, args, kwargs):
         secs = next(x.parts for x in (cond, a, b) if x.rng is not None).keys()
         pick = lambda x, s: x.parts if x.rng is None else x.parts[s]
         return Sym(ctx, rng, {s: g.op("sel", pick(cond, s), pick(a, s), pick(b, s)) for s in secs})
+    if name in ("zeros_like", "ones_like", "full_like") and len(args) >= 1 and isinstance(args[0], Sym):
+        value = 0.0 if name == "zeros_like" else 1.0 if name == "ones_like" else \
+            (args[1] if len(args) > 1 else kwargs["fill_value"])
+        x = args[0]                            # a constant with the node range of x (a select that always
+        return _apply_function(np.where, (x == x, value, value), {})     # takes `value`, also for NaN x)
+    if name in ("mean", "max", "min", "amax", "amin", "dot", "norm", "prod") and len(args) >= 1 and is_sym(args[0]) \
+            and not kwargs:
+        # reductions over the nodes are not node-local: expanded element by element (scalar rows / cost)
+        items = SymList.from_any(args[0]).items
+        if name == "mean":
+            return _apply_function(np.sum, (args[0],), {}) / float(len(items))
+        if name in ("max", "amax", "min", "amin"):
+            uf = "maximum" if name in ("max", "amax") else "minimum"
+            acc = items[0]
+            for e in items[1:]:
+                acc = _apply_ufunc(uf, (acc, e))
+            return acc
+        if name == "prod":
+            acc = items[0]
+            for e in items[1:]:
+                acc = acc * e
+            return acc
+        if name == "dot" and len(args) == 2:
+            other = SymList.from_any(args[1], len(items), args[0].ctx).items
+            acc = items[0] * other[0]
+            for a_, b_ in zip(items[1:], other[1:]):
+                acc = acc + a_ * b_
+            return acc
+        if name == "norm" and len(args) == 1:
+            acc = items[0] * items[0]
+            for e in items[1:]:
+                acc = acc + e * e
+            return _apply_ufunc("sqrt", (acc,))
     if name == "clip" and len(args) + len(kwargs) >= 2 and is_sym(args[0]):
         lo = args[1] if len(args) > 1 else kwargs.get("a_min", kwargs.get("min"))
         hi = args[2] if len(args) > 2 else kwargs.get("a_max", kwargs.get("max"))

@@ -143,3 +143,67 @@ def test_random_callbacks_on_the_device(api, seed):
             continue
         assert_c_close(c[b], c_ref, J_ref, np.clip(P[b], lb, ub))
         assert_J_close(J[b].T, J_ref, dust=1e-6)
+
+
+def _small_problem(mod, f, g):
+    prob = mod.Problem([0.0, 1.0], [6], [2], [1], 3)
+
+    def dyn(prob, obj, section):
+        x, y, u = prob.states(0, section), prob.states(1, section), prob.controls(0, section)
+        d = mod.Dynamics(prob, section)
+        d[0] = f(x, y, u)
+        d[1] = u
+        return d()
+
+    def eq(p, o):
+        r = mod.Condition()
+        r.equal(p.states(0, 0)[0], 0.3)
+        return r()
+
+    prob.dynamics = [dyn]
+    prob.knot_states_smooth = []
+    prob.cost = lambda p, o: p.time_final(-1) + g(p.states(0, 0), p.states(1, 0))
+    prob.equality = eq
+    prob.inequality = lambda p, o: mod.Condition()()
+    prob.set_states(0, 0, np.linspace(0.3, 0.9, 6))
+    prob.set_states(1, 0, np.linspace(1.2, 2.1, 6))
+    prob.set_controls(0, 0, np.linspace(-0.4, 0.5, 6))
+    return prob
+
+
+IDIOMS = {
+    "like": (lambda x, y, u: np.zeros_like(x) + y * np.ones_like(x) + np.full_like(x, 2.5) * u, lambda x, y: 0.0),
+    "expm1_log1p": (lambda x, y, u: np.expm1(x) + np.log1p(y * y), lambda x, y: 0.0),
+    "isnan_heaviside": (lambda x, y, u: np.where(np.isnan(x), 0.0, x) + np.heaviside(u, 0.5) * y, lambda x, y: 0.0),
+    "mod_fmod": (lambda x, y, u: np.mod(3.7 * x + u, 0.8) + np.fmod(5.3 * u - 0.1, 0.7) + np.remainder(y, 0.9),
+                 lambda x, y: 0.0),
+    "reductions_in_cost": (lambda x, y, u: x * y,
+                           lambda x, y: np.mean(x) + 0.1 * np.max(y) - 0.2 * np.min(x) + 0.01 * np.dot(x, y)
+                           + 0.05 * np.linalg.norm(y) + 0.001 * np.prod(x)),
+    "python_builtins": (lambda x, y, u: abs(x) + pow(y, 2) + x.copy() * len(x) + x.shape[0] * u, lambda x, y: 0.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(IDIOMS))
+def test_numpy_idioms_trace_and_match(api, name):
+    """Common numpy idioms in user callbacks (constructors, expm1 / log1p, isnan, heaviside, mod / fmod,
+    reductions over the nodes inside a cost) lower to tape operations that reproduce numpy."""
+    f, g = IDIOMS[name]
+    pa, po = _small_problem(api, f, g), _small_problem(og_numpy, f, g)
+    lb, ub = og_numpy.bounds_arrays(po)
+    emu = EmuProblem(tape.build_ir(pa, None), lb, ub)
+    P = np.asarray(po.p)[None] * (1.0 + 0.03 * np.random.default_rng(1).standard_normal((2, len(po.p))))
+    c, J = emu.eval_fd(P)
+    for b in range(2):
+        c_ref, J_ref = og_numpy.eval_fd(po, None, P[b], lb, ub)
+        assert_c_close(c[b], c_ref, J_ref, P[b])
+        assert_J_close(J[b].T, J_ref, dust=1e-6)
+
+
+def test_node_reductions_inside_dynamics_are_rejected(api):
+    """A reduction over the nodes inside `dynamics` is not node-local: the tracer says so instead of
+    producing a dense Jacobian block the kernels do not model."""
+    from opengoddard_b200 import trace
+    pa = _small_problem(api, lambda x, y, u: y + np.sum(x), lambda x, y: 0.0)
+    with pytest.raises(trace.TraceError):
+        tape.build_ir(pa, None)
