@@ -125,3 +125,29 @@ def test_product_never_imports_the_oracle_or_the_reference():
             "opengoddard_b200.sqp, opengoddard_b200.batch; "
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
     subprocess.run([sys.executable, "-c", code], check=True, timeout=300)
+
+
+def test_jit_disk_cache_is_opt_in_and_hits(api, tmp_path, monkeypatch):
+    """$OGB200_JIT_CACHE: the NVRTC result is stored under a key made of the generated source, the
+    embedded headers, the kernel variant and the library version; a second compile is a file read."""
+    import time
+    from opengoddard_b200 import tape, workloads
+    wl = workloads.build("cfg3_goddard_knot30x2", api)
+    ir = tape.build_ir(wl.prob, wl.obj)
+    try:
+        n0, _ = capi.jit_check(ir)                       # no cache configured: nothing is written anywhere
+    except capi.OgbError as e:
+        if "libnvrtc not found" in str(e):
+            pytest.skip("NVRTC is not installed here")
+        raise
+    assert list(tmp_path.iterdir()) == []
+    monkeypatch.setenv("OGB200_JIT_CACHE", str(tmp_path))
+    n1, _ = capi.jit_check(ir)
+    files = list(tmp_path.iterdir())
+    assert len(files) == 1 and files[0].name.startswith("ogb200_") and files[0].name.endswith(".cubin")
+    t0 = time.perf_counter()
+    n2, _ = capi.jit_check(ir)
+    assert time.perf_counter() - t0 < 0.5 and n0 == n1 == n2
+    other = workloads.build("cfg2_goddard50", api)       # a different problem gets a different entry
+    capi.jit_check(tape.build_ir(other.prob, other.obj))
+    assert len(list(tmp_path.iterdir())) == 2

@@ -299,3 +299,25 @@ def test_autotune_keeps_results_bit_identical(torch_cuda, api):
         c2, J2 = eng.eval_fd(P)
         assert torch_cuda.equal(c0, c2) and torch_cuda.equal(J0, J2)
         assert torch_cuda.equal(eng.eval(P), c0)
+
+
+def test_kernel_loaded_from_the_disk_cache_is_the_same_kernel(torch_cuda, tmp_path):
+    """Two fresh processes with $OGB200_JIT_CACHE: the second loads the cubin the first one stored and
+    produces bit-identical c and J."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    from tests.helpers import ROOT
+    code = ("import sys, hashlib; sys.path.insert(0, %r); import torch; import OpenGoddard.optimize as api; "
+            "from opengoddard_b200 import workloads; wl = workloads.build('cfg3_goddard_knot30x2', api); "
+            "eng = wl.prob.compile(wl.obj); assert eng.info.jit == 1; c, J = eng.eval_fd(workloads.make_batch(wl, 7)); "
+            "print(hashlib.sha256(c.cpu().numpy().tobytes() + J.cpu().numpy().tobytes()).hexdigest())" % ROOT)
+    env = dict(os.environ, OGB200_JIT_CACHE=str(tmp_path))
+    outs = []
+    for k in range(2):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+        assert len(list(tmp_path.iterdir())) == 1
+    assert outs[0] == outs[1] and len(outs[0]) == 64
