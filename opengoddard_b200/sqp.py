@@ -210,7 +210,10 @@ class WorkerPool:
                 for w in range(self.W):
                     self.procs.append(subprocess.Popen([sys.executable, "-m", "opengoddard_b200.sqp_worker", address],
                                                        env=env, stdin=subprocess.DEVNULL))
-                listener._listener._socket.settimeout(120.0)
+                try:                                   # do not wait for ever for a worker that failed to start
+                    listener._listener._socket.settimeout(120.0)
+                except AttributeError:                 # (private attributes of multiprocessing.connection)
+                    pass
                 for w in range(self.W):
                     self.conns.append(listener.accept())
         except Exception:
