@@ -342,16 +342,19 @@ class _HostEvaluator:
         c = self.eng.eval(t.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.eng.device))
         return c.cpu().numpy()
 
-    def eval_fd(self, X):
+    accepts_out = True            # eval_fd(X, out_J=...) writes the Jacobians straight into the caller's buffer
+
+    def eval_fd(self, X, out_J=None):
         """c (k, M) and the dense J (k, n, M) in host memory through the host-buffer session
-        (packed device->host transport, ogb_host_eval_fd)."""
+        (packed device->host transport, ogb_host_eval_fd).  out_J: a C-contiguous (k, n, M) float64
+        array (e.g. a slice of the SQP driver's shared-memory block) that receives J."""
         X = np.ascontiguousarray(X, dtype=np.float64)
         k = X.shape[0]
         if self.session is None or self.session.max_batch < k:
             if self.session is not None:
                 self.session.close()
             self.session = self.eng.host_session(max(k, 16))
-        return self.session.eval_fd(X, mode="dense")
+        return self.session.eval_fd(X, J=out_J, mode="dense")
 
 
 def lgl_device(N, device="cuda:0"):

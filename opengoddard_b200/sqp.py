@@ -94,6 +94,9 @@ class _LocalStepper:
         it = self.inst[b]
         self._slsqp(it.state, it.fx, it.g, it.C, it.d, it.x, it.mult, self.xl, self.xu, it.buffer, it.indices)
 
+    def normals_buffer(self, ids):
+        return None                  # (the per-instance C matrices are filled from the evaluator's array)
+
     def step(self, active):
         if self.pool is not None:
             list(self.pool.map(self._step, active))
@@ -290,9 +293,17 @@ class _ProcessStepper:
         self.arr["D"][np.asarray(ids, dtype=np.int64)] = c
         self._vals = list(ids)
 
+    def normals_buffer(self, ids):
+        """The shared-memory block that will hold the Jacobians of `ids`, if they are one contiguous run
+        of instances: the evaluator then writes them there itself (no copy through this process)."""
+        if len(ids) and ids[-1] - ids[0] + 1 == len(ids):
+            return self.arr["J"][ids[0]:ids[-1] + 1]
+        return None
+
     def put_normals(self, ids, J, G):
         idx = np.asarray(ids, dtype=np.int64)
-        self.arr["J"][idx] = J
+        if not (isinstance(J, np.ndarray) and J.base is not None and np.shares_memory(J, self.arr["J"])):
+            self.arr["J"][idx] = J
         self._use_g = G is not None
         if G is not None:
             self.arr["G"][idx] = G
@@ -381,7 +392,10 @@ def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_g
     try:
         # mode 0 on entry: objective, constraints and gradients at the start point
         ids = list(range(B))
-        c, J = evaluator.eval_fd(np.stack([st.x(b) for b in ids]))
+        direct = bool(getattr(evaluator, "accepts_out", False))
+        buf = st.normals_buffer(ids) if direct else None
+        X_all = np.stack([st.x(b) for b in ids])
+        c, J = evaluator.eval_fd(X_all, out_J=buf) if buf is not None else evaluator.eval_fd(X_all)
         st.put_values(ids, c)
         st.put_normals(ids, J, grads(ids))
         nfev += 1
@@ -400,7 +414,8 @@ def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_g
                 nfev[need_f] += 1
             if need_g:
                 Xg = np.stack([st.x(b) for b in need_g])
-                _, Jg = evaluator.eval_fd(Xg)
+                buf = st.normals_buffer(need_g) if direct else None
+                _, Jg = evaluator.eval_fd(Xg, out_J=buf) if buf is not None else evaluator.eval_fd(Xg)
                 st.put_normals(need_g, Jg, grads(need_g))
                 njev[need_g] += 1
             if callback is not None:

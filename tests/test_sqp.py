@@ -148,3 +148,41 @@ def test_worker_pool_is_reusable_across_solves():
             assert np.array_equal(one["x"], two["x"]) and np.array_equal(one["status"], two["status"])
         assert all(pr.poll() is None for pr in pool.procs)       # still alive between calls
     assert pool.procs == []
+
+
+class OutEvaluator(OracleEvaluator):
+    """Like the device evaluator: can write the Jacobians into a buffer the driver hands it."""
+    accepts_out = True
+
+    def __init__(self, wl):
+        super().__init__(wl)
+        self.direct = 0
+
+    def eval_fd(self, X, out_J=None):
+        c, J = super().eval_fd(X)
+        if out_J is None:
+            return c, J
+        assert out_J.shape == J.shape and out_J.flags.c_contiguous
+        out_J[...] = J
+        self.direct += 1
+        return c, out_J
+
+
+def test_evaluator_writes_jacobians_straight_into_shared_memory():
+    """With worker processes and an evaluator that accepts a destination, a round in which a contiguous
+    run of instances asks for gradients has its Jacobians written into the shared block directly."""
+    from threadpoolctl import threadpool_limits
+    wl = workloads.build("cfg1_brachistochrone20", og_numpy)
+    meq, mineq = 64, 41
+    P = workloads.make_batch(wl, 4)
+    ev1, ev2 = OracleEvaluator(wl), OutEvaluator(wl)
+    with threadpool_limits(1):
+        one = sqp.slsqp_batch(ev1, P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5)
+    two = sqp.slsqp_batch(ev2, P, ev2.lb, ev2.ub, meq, mineq, ftol=1e-6, maxiter=5, processes=2)
+    assert ev2.direct >= 1
+    for key in ("x", "fun", "status", "nit"):
+        assert np.array_equal(one[key], two[key]), key
+    three = sqp.slsqp_batch(OutEvaluator(wl), P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5)   # local stepper
+    with threadpool_limits(1):
+        four = sqp.slsqp_batch(OutEvaluator(wl), P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5)
+    assert np.array_equal(four["x"], one["x"]) and three["x"].shape == one["x"].shape
