@@ -141,3 +141,23 @@ def test_facade_evaluate_batch_host(api):
     c_h, J_h = wl.prob.evaluate_batch(P, wl.obj, host=True)
     assert isinstance(c_h, np.ndarray) and (c_h == c_d.cpu().numpy()).all() and (J_h == J_d.cpu().numpy()).all()
     assert (wl.prob.evaluate_batch(P, wl.obj, jacobian=False, host=True) == c_h).all()
+
+
+@pytest.mark.parametrize("isa", ["0", "1", "2"])
+def test_expand_dense_every_store_flavour(monkeypatch, isa):
+    """SSE2 / AVX2 / AVX-512 non-temporal store paths of the host expansion ($OGB200_HOST_ISA; a flavour
+    the CPU lacks falls back to the next one) give the same bytes, for aligned and unaligned rows and
+    for patterns with long zero runs, dense runs and values in the first / last line."""
+    monkeypatch.setenv("OGB200_HOST_ISA", isa)
+    rng = np.random.default_rng(int(isa) + 11)
+    for nM, runs in ((4099, [(0, 3), (17, 40), (4000, 99)]), (1000, [(5, 1), (999, 1)]), (65, [(0, 65)]), (9, [])):
+        lin = np.array(sorted({p for a, k in runs for p in range(a, min(nM, a + k))}), dtype=np.uint32)
+        B = 3
+        vals = rng.standard_normal((B, len(lin)))
+        ref = np.zeros((B, nM))
+        ref[:, lin] = vals
+        for shift in (0, 1, 5):
+            raw = np.full(B * nM + shift + 8, -9.0)
+            out = raw[shift:shift + B * nM].reshape(B, nM)
+            capi.host_expand(vals, lin, nM, out=out, mode="dense", threads=2)
+            assert (out == ref).all() and (raw[:shift] == -9.0).all() and (raw[shift + B * nM:] == -9.0).all()
