@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OGB_VERSION 110
+#define OGB_VERSION 200
 
 /* ---- expression tapes -----------------------------------------------------
  * User callbacks (dynamics / equality / inequality / cost / running_cost; reference
@@ -129,6 +129,8 @@ typedef struct ogb_problem_info {
     int32_t smem_bytes; /* dynamic shared memory of the sweep kernel                  */
     int32_t ctas_per_sm;
     int32_t jit;        /* 1: the tapes were compiled into the sweep kernel with NVRTC      */
+    int32_t nnz;        /* structural non-zeros of one instance's J, -1 until the pattern is known   */
+    int64_t launches;   /* kernels launched through this handle so far (counted where they are launched) */
 } ogb_problem_info;
 
 const char* ogb_last_error(void);
@@ -165,6 +167,12 @@ enum ogb_option {
                                     into more, smaller work items (bit-identical results, better balance)  */
     OGB_OPT_PROBE_MODE = 8,      /* timing probes only (J is NOT a Jacobian afterwards): 2 = no zero stream,
                                     3 = zero stream only, 4 = no column output at all; 0 = normal             */
+    OGB_OPT_SPLIT = 9,           /* how ogb_eval_fd produces the dense J: 0 = the fused sweep kernel (one launch after
+                                    K1), 1 = the split pipeline (K1 -> K2a packed sweep on an internal stream, K2b
+                                    densify on the caller's stream, chunk by chunk), -1 (default) = split for batches
+                                    of >= 256 MB of dense J.  Results are bit-identical either way.                */
+    OGB_OPT_SPLIT_CHUNK = 10,    /* instances per chunk of the split pipeline (0 = auto, ~192 MB of dense J)        */
+    OGB_OPT_DENSE_STREAMING = 11,/* 1 (default): K2b writes its zeros with st.global.cs (evict-first)              */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
                                     launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
                                     (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */
@@ -208,6 +216,17 @@ int ogb_eval(void* prob, const double* p, int B, double* c, void* work, void* st
 int ogb_eval_fd(void* prob, const double* p, const double* lb, const double* ub,
                 double abs_step, int B, double* c, double* J, void* work, void* stream);
 
+/* ---- sparse evaluation -------------------------------------------------------------------
+ * ogb_eval_sparse = ogb_eval_fd without the dense Jacobian: c [B, nrows] and vals [B, nnz], the
+ * structurally non-zero entries of every instance's FD Jacobian in the ogb_jac_pattern layout
+ * (K1 + the sweep kernel writing packed output; bit-identical to the same entries of ogb_eval_fd's
+ * J).  ogb_densify (kernel K2b) expands packed values into the dense J [B, nvars, nrows], zeros
+ * included; ogb_eval_fd's split pipeline is the two chained chunk by chunk.  Replaces the same
+ * reference code as ogb_eval_fd (scipy/optimize/_slsqp_py.py:353-367 on optimize.py:670-715).      */
+int ogb_eval_sparse(void* prob, const double* p, const double* lb, const double* ub, double abs_step,
+                    int B, double* c, double* vals, void* work, void* stream);
+int ogb_densify(void* prob, const double* vals, int B, double* J, void* stream);
+
 /* ---- packed Jacobian transport ---------------------------------------------------------
  * The FD Jacobian is structurally sparse: a perturbed state moves its own defect rows and the
  * rows living at its node (eq J 7 758 / 31 155, ineq J 301 / 60 501
@@ -226,9 +245,9 @@ int ogb_pack(void* prob, const double* J, int B, double* vals, void* stream);
  * scratch, two CUDA streams, pinned staging and a pool of host threads for one problem on the
  * current device.  ogb_host_eval_fd is synchronous: when it returns, c_h [B, nrows] and J_h
  * are complete.  The batch is cut into chunks that flow through
- *     H2D p -> K1 -> K2 (dense J in HBM) -> K3 pack -> D2H packed values -> host threads
- * write the dense J_h (zeros with non-temporal stores + the packed non-zeros), so PCIe carries
- * nnz instead of nvars * nrows doubles per instance and the copies overlap the kernels.
+ *     H2D p -> K1 -> K2a (sweep kernel, packed output) -> D2H packed values -> host threads
+ * write the dense J_h (zeros with non-temporal stores + the packed non-zeros), so neither HBM nor
+ * PCIe ever carries more than nnz doubles per instance and the copies overlap the kernels.
  * p_h / c_h / J_h may be pageable or pinned memory.                                        */
 enum ogb_host_mode {
     OGB_HOST_J_DENSE = 0,      /* J_h [B, nvars, nrows] fully rewritten (zeros included)              */
@@ -252,6 +271,18 @@ void  ogb_host_session_destroy(void* session);
 int   ogb_host_eval_fd(void* session, const double* p_h, const double* lb_h, const double* ub_h,
                        double abs_step, int B, double* c_h, double* J_h, int mode);
 int   ogb_host_session_stats(void* session, ogb_host_stats* out);
+
+/* The same evaluation delivered straight into an SQP driver's own buffers -- what SciPy's
+ * _eval_con_normals does per instance with `C[row:row+k, :] = jac(x)` (scipy/optimize/
+ * _slsqp_py.py:599-615) and `g = sf.grad(x)` (:533): instance b's packed non-zeros are scattered into
+ * the Fortran-ordered matrix C_h[b] (leading dimension ld >= mrows; entry (r, j) at C_h[b][j * ld + r])
+ * for the rows r < mrows (mrows = meq + mineq: every constraint row), and the cost row (r = nrows - 1)
+ * into the vector g_h[b][j] (g_h: B pointers, or NULL).  Only structural non-zeros are written: the matrices must
+ * hold this problem's zero background (they do if they were zero-initialised and only ever written by
+ * this call; SLSQP's core does not modify C).  c_h [B, nrows] as in ogb_host_eval_fd.              */
+int   ogb_host_eval_fd_scatter(void* session, const double* p_h, const double* lb_h, const double* ub_h,
+                               double abs_step, int B, double* c_h, double* const* C_h, int ld, int mrows,
+                               double* const* g_h);
 
 /* The host half of the transport by itself (no GPU involved): expand packed values [B, nnz] into
  * dense J_h [B, nM] (mode OGB_HOST_J_DENSE or OGB_HOST_J_KEEP_ZEROS) with `threads` threads.   */

@@ -52,7 +52,8 @@ class OgbProblemDesc(C.Structure):
 
 class OgbProblemInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("nvars", "meq", "mineq", "nrows", "ndx", "total_nodes",
-                                          "tile_cols", "group_cols", "smem_bytes", "ctas_per_sm", "jit")]
+                                          "tile_cols", "group_cols", "smem_bytes", "ctas_per_sm", "jit",
+                                          "nnz")] + [("launches", C.c_int64)]
 
 
 class OgbHostStats(C.Structure):
@@ -177,6 +178,12 @@ def ogb():
         L.ogb_eval.argtypes = [vp, dp, i32, dp, vp, vp]
         L.ogb_eval_fd.restype = C.c_int
         L.ogb_eval_fd.argtypes = [vp, dp, dp, dp, C.c_double, i32, dp, dp, vp, vp]
+        L.ogb_eval_sparse.restype = C.c_int
+        L.ogb_eval_sparse.argtypes = [vp, dp, dp, dp, C.c_double, i32, dp, dp, vp, vp]
+        L.ogb_densify.restype = C.c_int
+        L.ogb_densify.argtypes = [vp, dp, i32, dp, vp]
+        L.ogb_host_eval_fd_scatter.restype = C.c_int
+        L.ogb_host_eval_fd_scatter.argtypes = [vp, vp, vp, vp, C.c_double, i32, vp, vp, i32, i32, vp]
         L.ogb_jac_pattern.restype = C.c_int
         L.ogb_jac_pattern.argtypes = [vp, vp, i32]
         L.ogb_pack.restype = C.c_int

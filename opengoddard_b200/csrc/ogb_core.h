@@ -80,6 +80,13 @@ struct OgbProb {
     const ogb_table* tables;    // lookup tables of OGB_INTERP
     const double* tab_x;
     const double* tab_y;
+    // sparse (packed) Jacobian layout, filled in once the structure probe has run (ogb_jac_pattern):
+    // entry e of an instance's packed values is J[prow[e], column of e]; column j owns entries
+    // [colptr[j], colptr[j+1]) in ascending row order; pmap[j * M + r] = e, or -1 for a structural zero
+    int nnz, pad_nnz;
+    const int* pmap;
+    const int* colptr;
+    const int* prow;
 };
 
 struct OgbWork {            // per work item scratch (shared memory on the device)
@@ -514,22 +521,33 @@ struct OgbColOut {
         if (r < meq) dense[r] = v; else tail[r - meq] = v;
     }
 };
+// ... or the packed values of the instance: entry pm[r] of vals (pm = pmap + j * M)
+struct OgbColPacked {
+    double* vals;
+    const int* pm;
+    OGB_HD void put(int r, double v) const {
+        const int e = pm[r];
+        if (e >= 0) vals[e] = v;
+    }
+};
 
 // rows of state `a` at every node i != k: only D[i,k] * delta moves
+template <class Out>
 OGB_HD void ogb_scatter_drows(const OgbProb& P, const OgbWork& W, const OgbSec& S, int a, int k,
-                              double dlt, double dx, double rdx, const OgbColOut& col, int lane, int nlanes) {
+                              double dlt, double dx, double rdx, const Out& col, int lane, int nlanes) {
     const double* Dt = P.Dt + S.doff + k * S.N;                // column k of D
     for (int i = lane; i < S.N; i += nlanes) {
         if (i == k) continue;
         const int e = S.dxoff + a * S.N + i;
         const double cp = (W.sdx[e] + Dt[i] * dlt) - W.cf[e];
-        col.dense[S.rdef + a * S.N + i] = ogb_fd_div(cp - W.sc[S.rdef + a * S.N + i], dx, rdx);
+        col.put(S.rdef + a * S.N + i, ogb_fd_div(cp - W.sc[S.rdef + a * S.N + i], dx, rdx));
     }
 }
 
 // rows living at node k: every state's defect row (dynamics moved) and the pointwise user rows
+template <class Out>
 OGB_HD void ogb_scatter_noderows(const OgbProb& P, const OgbWork& W, const OgbSec& S, int sidx, int a, int k,
-                                 int cl, double dlt, double dx, double rdx, const OgbColOut& col, int lane, int nlanes) {
+                                 int cl, double dlt, double dx, double rdx, const Out& col, int lane, int nlanes) {
     const double coef = W.coef[3 * sidx];
     const int g = S.g0 + k;
     for (int slot = lane; slot < S.nouts; slot += nlanes) {
@@ -538,7 +556,7 @@ OGB_HD void ogb_scatter_noderows(const OgbProb& P, const OgbWork& W, const OgbSe
             double dxp = W.sdx[S.dxoff + e];
             if (slot == a) dxp = dxp + P.D[S.doff + k * S.N + k] * dlt;
             const double cp = dxp - coef * W.pert[slot * W.G + cl];
-            col.dense[S.rdef + e] = ogb_fd_div(cp - W.sc[S.rdef + e], dx, rdx);
+            col.put(S.rdef + e, ogb_fd_div(cp - W.sc[S.rdef + e], dx, rdx));
         } else {
             const ogb_out o = P.outs[S.out_off + slot];
             if ((o.kind == OGB_OUT_EQ_POINT || o.kind == OGB_OUT_INEQ_POINT) && g >= o.glo && g < o.ghi) {
@@ -549,22 +567,24 @@ OGB_HD void ogb_scatter_noderows(const OgbProb& P, const OgbWork& W, const OgbSe
     }
 }
 
+template <class Out>
 OGB_HD void ogb_scatter_knots(const OgbProb& P, const OgbWork& W, int j, double x1, double dx,
-                              double rdx, const OgbColOut& col, int lane, int nlanes) {
+                              double rdx, const Out& col, int lane, int nlanes) {
     for (int t = lane; t < P.nknot; t += nlanes) {
         const OgbKnot K = P.knots[t];
         if (K.var_prev == j || K.var_post == j) {
             const double xp = K.var_prev == j ? x1 : W.sp[K.var_prev];
             const double xq = K.var_post == j ? x1 : W.sp[K.var_post];
             const double cp = ogb_nd(xp, K.u_prev) - (xq * K.u_post) / K.u_prev;
-            col.dense[K.row] = ogb_fd_div(cp - W.sc[K.row], dx, rdx);
+            col.put(K.row, ogb_fd_div(cp - W.sc[K.row], dx, rdx));
         }
     }
 }
 
 // a final-time variable: the defects of its own phase and of the next one rescale
+template <class Out>
 OGB_HD void ogb_scatter_time(const OgbProb& P, const OgbWork& W, int j, int sec, double x1, double dx,
-                             double rdx, const OgbColOut& col, int lane, int nlanes) {
+                             double rdx, const Out& col, int lane, int nlanes) {
     const double tfx1 = ogb_nd(x1, P.unit_time);
     for (int s = sec; s < P.nsec && s <= sec + 1; ++s) {
         const OgbSec& S = ogb_sec(P, s);
@@ -575,14 +595,15 @@ OGB_HD void ogb_scatter_time(const OgbProb& P, const OgbWork& W, int j, int sec,
         for (int e = lane; e < S.ns * S.N; e += nlanes) {
             const int b = e / S.N, i = e - b * S.N;
             const double cp = W.sdx[S.dxoff + e] - coef1 * W.sbase[b * P.gtot + S.g0 + i];
-            col.dense[S.rdef + e] = ogb_fd_div(cp - W.sc[S.rdef + e], dx, rdx);
+            col.put(S.rdef + e, ogb_fd_div(cp - W.sc[S.rdef + e], dx, rdx));
         }
     }
 }
 
 // rows of the scalar program (picked variables only) and the cost row (the "+1" row)
+template <class Out>
 OGB_HD void ogb_scatter_scalar_cost(const OgbProb& P, const OgbWork& W, const OgbCol& cd, int cl,
-                                    double dx, double rdx, const OgbColOut& col, int lane, int nlanes) {
+                                    double dx, double rdx, const Out& col, int lane, int nlanes) {
     if (cd.pick >= 0) {
         for (int slot = lane; slot < P.sc_nouts; slot += nlanes) {
             const ogb_out o = P.outs[P.sc_out_off + slot];
@@ -593,8 +614,9 @@ OGB_HD void ogb_scatter_scalar_cost(const OgbProb& P, const OgbWork& W, const Og
     if (lane == 0 && ogb_col_moves_cost(P, cd)) col.put(P.M - 1, ogb_fd_div(W.costp[cl] - W.sc[P.M - 1], dx, rdx));
 }
 
+template <class Out>
 OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl,
-                               const OgbColOut& col, int lane, int nlanes) {
+                               const Out& col, int lane, int nlanes) {
     const OgbCol cd = W.pcol[cl];
     const double dx = W.pdx[cl], rdx = W.prdx[cl];
     const double x1 = W.px1[cl];

@@ -127,7 +127,24 @@ struct Job {
     int nnz = 0, M = 0, B = 0, chunk = 1, mode = 0;
     size_t nM = 0;
     int isa = 0;
+    // mode OGB_HOST_J_SCATTER: packed entry e of instance b goes to C_dst[b][soff[e]] (soff >= 0) or
+    // to g_dst[b][-1 - soff[e]] (the cost row), or nowhere (soff = INT64_MIN)
+    double* const* C_dst = nullptr;
+    double* const* g_dst = nullptr;
+    const int64_t* soff = nullptr;
+    int n = 0;
 };
+
+constexpr int kScatterMode = 100;       // internal: ogb_host_eval_fd_scatter
+constexpr int64_t kNowhere = INT64_MIN;
+
+void expand_scatter(double* C, double* g, const double* vals, const int64_t* soff, int nnz) {
+    for (int e = 0; e < nnz; ++e) {
+        const int64_t o = soff[e];
+        if (o >= 0) C[o] = vals[e];
+        else if (o != kNowhere && g) g[-1 - o] = vals[e];
+    }
+}
 
 class Pool {
 public:
@@ -153,7 +170,8 @@ public:
         if (j.c_dst) std::memcpy(j.c_dst + (size_t)b * j.M, j.c_src + (size_t)b * j.M, (size_t)j.M * sizeof(double));
         if (!j.vals) return;
         const double* v = j.vals + (size_t)b * j.nnz;
-        if (j.mode == OGB_HOST_J_DENSE) expand_dense(j.J_dst + (size_t)b * j.nM, j.nM, v, j.lin, j.nnz, j.isa);
+        if (j.mode == kScatterMode) expand_scatter(j.C_dst[b], j.g_dst ? j.g_dst[b] : nullptr, v, j.soff, j.nnz);
+        else if (j.mode == OGB_HOST_J_DENSE) expand_dense(j.J_dst + (size_t)b * j.nM, j.nM, v, j.lin, j.nnz, j.isa);
         else if (j.mode == OGB_HOST_J_KEEP_ZEROS) expand_keep(j.J_dst + (size_t)b * j.nM, v, j.lin, j.nnz);
         else std::memcpy(j.J_dst + (size_t)b * j.nnz, v, (size_t)j.nnz * sizeof(double));
     }
@@ -209,7 +227,10 @@ struct Session {
     int isa = 0;
     // device
     double *p_d = nullptr, *lb_d = nullptr, *ub_d = nullptr, *c_d = nullptr, *vals_d = nullptr;
-    double *J_d = nullptr, *DX_d = nullptr, *Jfull_d = nullptr;
+    double *DX_d = nullptr, *Jfull_d = nullptr;
+    size_t work_bytes = 0;
+    std::vector<int64_t> soff;      // scatter offsets of the last ogb_host_eval_fd_scatter layout
+    int soff_ld = -1, soff_mrows = -1;
     // pinned staging
     double *p_s = nullptr, *c_s = nullptr, *vals_s = nullptr, *b_s = nullptr;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -220,7 +241,7 @@ struct Session {
     ~Session() {
         delete pool;
         cudaSetDevice(device);
-        for (double* d : {p_d, lb_d, ub_d, c_d, vals_d, J_d, DX_d, Jfull_d}) cudaFree(d);
+        for (double* d : {p_d, lb_d, ub_d, c_d, vals_d, DX_d, Jfull_d}) cudaFree(d);
         for (double* h : {p_s, c_s, vals_s, b_s}) cudaFreeHost(h);
         for (cudaEvent_t e : ev_done) cudaEventDestroy(e);
         for (cudaEvent_t e : ev_copied) cudaEventDestroy(e);
@@ -247,10 +268,11 @@ int session_init(Session* S, void* prob, int max_batch, int chunk, int threads) 
     if (ogb_jac_pattern(prob, S->lin.data(), S->nnz) < 0) return -1;
     S->maxB = max_batch;
     if (chunk <= 0) {
-        // default: ~256 MB of dense J per chunk, at least 64 instances, at most 8 chunks in flight
-        size_t per = S->nM * sizeof(double);
-        chunk = (int)std::max<size_t>(64, (256u << 20) / std::max<size_t>(1, per));
-        chunk = std::max(chunk, (max_batch + 15) / 16);
+        // default: ~12 chunks per full batch (each chunk's device->host copy overlaps the next chunk's
+        // kernels and the host threads' work on the previous one), at least 32 MB of packed values each
+        size_t per = std::max<size_t>(1, (size_t)S->nnz * sizeof(double));
+        chunk = (int)std::max<size_t>(16, (32u << 20) / per);
+        chunk = std::max(chunk, (max_batch + 11) / 12);
     }
     S->chunk = std::min(chunk, max_batch);
     S->nchunks = (max_batch + S->chunk - 1) / S->chunk;
@@ -261,8 +283,8 @@ int session_init(Session* S, void* prob, int max_batch, int chunk, int threads) 
     HCUDA(cudaMalloc((void**)&S->ub_d, (size_t)n * 8));
     HCUDA(cudaMalloc((void**)&S->c_d, B * M * 8));
     HCUDA(cudaMalloc((void**)&S->vals_d, std::max<size_t>(1, B * S->nnz) * 8));
-    HCUDA(cudaMalloc((void**)&S->J_d, (size_t)S->chunk * S->nM * 8));
-    HCUDA(cudaMalloc((void**)&S->DX_d, std::max<size_t>(256, ogb_workspace_bytes(prob, S->chunk))));
+    S->work_bytes = std::max<size_t>(256, ogb_workspace_bytes(prob, S->chunk));
+    HCUDA(cudaMalloc((void**)&S->DX_d, S->work_bytes));
     HCUDA(cudaMallocHost((void**)&S->p_s, B * n * 8));
     HCUDA(cudaMallocHost((void**)&S->c_s, B * M * 8));
     HCUDA(cudaMallocHost((void**)&S->vals_s, std::max<size_t>(1, B * S->nnz) * 8));
@@ -300,21 +322,28 @@ int ogb_host_session_stats(void* h, ogb_host_stats* out) {
     return 0;
 }
 
-int ogb_host_eval_fd(void* h, const double* p_h, const double* lb_h, const double* ub_h, double abs_step,
-                     int B, double* c_h, double* J_h, int mode) {
-    Session* S = (Session*)h;
-    if (S && B == 0) return 0;
-    if (!S || !p_h || !lb_h || !ub_h || !c_h || !J_h) return fail("ogb_host_eval_fd: null argument");
-    if (B < 0 || B > S->maxB) return fail("ogb_host_eval_fd: batch larger than the session's max_batch");
-    if (mode < OGB_HOST_J_DENSE || mode > OGB_HOST_J_DMA) return fail("ogb_host_eval_fd: unknown mode");
-    if (!(abs_step > 0.0)) return fail("ogb_host_eval_fd: abs_step must be positive");
+// Shared body of ogb_host_eval_fd / ogb_host_eval_fd_scatter.  `job` arrives with its destination
+// fields (mode, J_dst or C_dst / g_dst / soff) filled in.
+static int host_eval_core(Session* S, const double* p_h, const double* lb_h, const double* ub_h, double abs_step,
+                          int B, double* c_h, double* J_h, Job job) {
     const double t0 = now_ms();
     HCUDA(cudaSetDevice(S->device));
     const int n = S->info.nvars, M = S->info.nrows, CH = S->chunk;
     const int nch = (B + CH - 1) / CH;
+    const int mode = job.mode;
     const bool dma = mode == OGB_HOST_J_DMA;
-    if (dma && !S->Jfull_d) HCUDA(cudaMalloc((void**)&S->Jfull_d, (size_t)S->maxB * S->nM * 8));
-    int launches = 0;
+    if (dma) {
+        if (!S->Jfull_d) HCUDA(cudaMalloc((void**)&S->Jfull_d, (size_t)S->maxB * S->nM * 8));
+        const size_t need = ogb_workspace_bytes(S->prob, S->chunk);      // (the dense path may want more scratch)
+        if (need > S->work_bytes) {
+            cudaFree(S->DX_d);
+            S->DX_d = nullptr;
+            HCUDA(cudaMalloc((void**)&S->DX_d, need));
+            S->work_bytes = need;
+        }
+    }
+    ogb_problem_info inf0{};
+    ogb_problem_info_get(S->prob, &inf0);
     int64_t h2d = 0, d2h = 0;
 
     std::memcpy(S->b_s, lb_h, (size_t)n * 8);
@@ -326,10 +355,9 @@ int ogb_host_eval_fd(void* h, const double* p_h, const double* lb_h, const doubl
     if (p_pinned) HCUDA(cudaMemcpyAsync(S->p_d, p_h, (size_t)B * n * 8, cudaMemcpyHostToDevice, S->s_compute));
     h2d += (int64_t)B * n * 8;
 
-    Job job;
     job.vals = dma ? nullptr : S->vals_s;
-    job.c_src = S->c_s; job.c_dst = c_h; job.J_dst = J_h; job.lin = S->lin.data();
-    job.nnz = S->nnz; job.M = M; job.B = B; job.chunk = CH; job.mode = mode; job.nM = S->nM; job.isa = S->isa;
+    job.c_src = S->c_s; job.c_dst = c_h; job.lin = S->lin.data();
+    job.nnz = S->nnz; job.M = M; job.B = B; job.chunk = CH; job.nM = S->nM; job.isa = S->isa; job.n = n;
     S->pool->start(job);
 
     int rc = 0;
@@ -340,19 +368,19 @@ int ogb_host_eval_fd(void* h, const double* p_h, const double* lb_h, const doubl
             std::memcpy(S->p_s + (size_t)b0 * n, p_h + (size_t)b0 * n, (size_t)nb * n * 8);
             if (cudaMemcpyAsync(pk, S->p_s + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, S->s_compute) != cudaSuccess) { rc = fail("H2D of p failed"); break; }
         }
-        double* Jk = dma ? S->Jfull_d + (size_t)b0 * S->nM : S->J_d;
         double* ck = S->c_d + (size_t)b0 * M;
-        rc = ogb_dx_gemm(S->prob, pk, S->lb_d, S->ub_d, nb, S->DX_d, S->s_compute);
-        if (!rc) rc = ogb_sweep(S->prob, pk, S->DX_d, S->lb_d, S->ub_d, abs_step, nb, ck, Jk, S->s_compute);
-        launches += 2;
-        if (!rc && !dma) { rc = ogb_pack(S->prob, Jk, nb, S->vals_d + (size_t)b0 * S->nnz, S->s_compute); ++launches; }
+        if (dma) {          // the plain dense transport: the dense J in HBM, one device -> host copy
+            rc = ogb_eval_fd(S->prob, pk, S->lb_d, S->ub_d, abs_step, nb, ck, S->Jfull_d + (size_t)b0 * S->nM, S->DX_d, S->s_compute);
+        } else {            // K1 + the sweep kernel with packed output: no dense J anywhere on the device
+            rc = ogb_eval_sparse(S->prob, pk, S->lb_d, S->ub_d, abs_step, nb, ck, S->vals_d + (size_t)b0 * S->nnz, S->DX_d, S->s_compute);
+        }
         if (rc) break;
         cudaEventRecord(S->ev_done[k], S->s_compute);
         cudaStreamWaitEvent(S->s_copy, S->ev_done[k], 0);
         cudaMemcpyAsync(S->c_s + (size_t)b0 * M, ck, (size_t)nb * M * 8, cudaMemcpyDeviceToHost, S->s_copy);
         d2h += (int64_t)nb * M * 8;
         if (dma) {
-            cudaMemcpyAsync(J_h + (size_t)b0 * S->nM, Jk, (size_t)nb * S->nM * 8, cudaMemcpyDeviceToHost, S->s_copy);
+            cudaMemcpyAsync(J_h + (size_t)b0 * S->nM, S->Jfull_d + (size_t)b0 * S->nM, (size_t)nb * S->nM * 8, cudaMemcpyDeviceToHost, S->s_copy);
             d2h += (int64_t)nb * S->nM * 8;
         } else {
             cudaMemcpyAsync(S->vals_s + (size_t)b0 * S->nnz, S->vals_d + (size_t)b0 * S->nnz,
@@ -375,10 +403,51 @@ int ogb_host_eval_fd(void* h, const double* p_h, const double* lb_h, const doubl
     S->pool->wait();
     if (rc) { cudaStreamSynchronize(S->s_compute); cudaStreamSynchronize(S->s_copy); return rc; }
     if (ce != cudaSuccess) return fail(std::string("ogb_host_eval_fd: ") + cudaGetErrorString(ce));
-    S->st.h2d_bytes = h2d; S->st.d2h_bytes = d2h; S->st.launches = launches; S->st.nnz = S->nnz;
+    ogb_problem_info inf1{};
+    ogb_problem_info_get(S->prob, &inf1);
+    S->st.h2d_bytes = h2d; S->st.d2h_bytes = d2h; S->st.launches = (int32_t)(inf1.launches - inf0.launches); S->st.nnz = S->nnz;
     S->st.chunk = CH; S->st.threads = S->pool->size(); S->st.nchunks = nch;
     S->st.ms_total = now_ms() - t0; S->st.ms_first_chunk = t_first;
     return 0;
+}
+
+int ogb_host_eval_fd(void* h, const double* p_h, const double* lb_h, const double* ub_h, double abs_step,
+                     int B, double* c_h, double* J_h, int mode) {
+    Session* S = (Session*)h;
+    if (S && B == 0) return 0;
+    if (!S || !p_h || !lb_h || !ub_h || !c_h || !J_h) return fail("ogb_host_eval_fd: null argument");
+    if (B < 0 || B > S->maxB) return fail("ogb_host_eval_fd: batch larger than the session's max_batch");
+    if (mode < OGB_HOST_J_DENSE || mode > OGB_HOST_J_DMA) return fail("ogb_host_eval_fd: unknown mode");
+    if (!(abs_step > 0.0)) return fail("ogb_host_eval_fd: abs_step must be positive");
+    Job job;
+    job.mode = mode;
+    job.J_dst = J_h;
+    return host_eval_core(S, p_h, lb_h, ub_h, abs_step, B, c_h, J_h, job);
+}
+
+int ogb_host_eval_fd_scatter(void* h, const double* p_h, const double* lb_h, const double* ub_h, double abs_step,
+                             int B, double* c_h, double* const* C_h, int ld, int mrows, double* const* g_h) {
+    Session* S = (Session*)h;
+    if (S && B == 0) return 0;
+    if (!S || !p_h || !lb_h || !ub_h || !c_h || !C_h) return fail("ogb_host_eval_fd_scatter: null argument");
+    if (B < 0 || B > S->maxB) return fail("ogb_host_eval_fd_scatter: batch larger than the session's max_batch");
+    if (!(abs_step > 0.0)) return fail("ogb_host_eval_fd_scatter: abs_step must be positive");
+    const int M = S->info.nrows;
+    if (mrows < 0 || mrows > M || ld < std::max(1, mrows)) return fail("ogb_host_eval_fd_scatter: need 0 <= mrows <= nrows and ld >= max(1, mrows)");
+    if (S->soff_ld != ld || S->soff_mrows != mrows) {      // destination offset of every packed entry, once per layout
+        S->soff.assign((size_t)std::max(1, S->nnz), kNowhere);
+        for (int e = 0; e < S->nnz; ++e) {
+            const uint32_t l = S->lin[e];
+            const int64_t j = l / (uint32_t)M, r = l - (uint32_t)j * (uint32_t)M;
+            if (r < mrows) S->soff[e] = j * (int64_t)ld + r;
+            else if (r == M - 1) S->soff[e] = -1 - j;
+        }
+        S->soff_ld = ld; S->soff_mrows = mrows;
+    }
+    Job job;
+    job.mode = kScatterMode;
+    job.C_dst = C_h; job.g_dst = g_h; job.soff = S->soff.data();
+    return host_eval_core(S, p_h, lb_h, ub_h, abs_step, B, c_h, nullptr, job);
 }
 
 int ogb_host_expand(const double* vals_h, const uint32_t* lin_h, int nnz, size_t nM, int B, double* J_h,

@@ -68,6 +68,7 @@ __device__ __forceinline__ const T* cache_copy(double*& cur, const T* src, size_
 }
 
 struct OgbSlot { int rbase, klo, khi, isdyn; };   // where output slot t of a node program lands
+template <bool V> struct OgbBool { static constexpr bool value = V; };
 
 #define OGB_FAST_MAXN 128      // register-cached row constants cover phases up to 128 nodes
 
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(OGB_MAX_THREADS, OGB_MIN_BLOCKS)
 ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const double* __restrict__ DX,
                  const double* __restrict__ lb, const double* __restrict__ ub, double abs_step,
                  int B, double* __restrict__ c, double* __restrict__ J, int with_fd,
-                 int ncode, int nconsts, int nouts, int force_generic, unsigned long long* ticket) {
+                 int ncode, int nconsts, int nouts, int force_generic, unsigned long long* ticket,
+                 unsigned long long ticket_base) {
     extern __shared__ __align__(16) double smem[];
 #ifdef OGB_SPEC_M                     // NVRTC build: the problem's sizes are compile-time constants
     P.M = OGB_SPEC_M; P.n = OGB_SPEC_NVARS; P.meq = OGB_SPEC_MEQ; P.mineq = OGB_SPEC_MINEQ;
@@ -165,7 +167,8 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             mbar_expect_tx(mbar + st, (uint32_t)(bp + bd) * 8u);
             if (bp) bulk_g2s(sp + hp, gp + hp, (uint32_t)bp * 8u, mbar + st);
             if (bd) bulk_g2s(sdx + hd, gdx + hd, (uint32_t)bd * 8u, mbar + st);
-        } else if (tid == 32 % nthr) {
+        }
+        if (tid == (nthr > 32 ? 32 : 0)) {      // (a one-warp CTA: thread 0 does both)
             if (hp) sp[0] = gp[0];
             for (int e = hp + bp; e < n; ++e) sp[e] = gp[e];
             if (!fused_dx) {
@@ -192,7 +195,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         const int st = (int)(it & 1u);
         long claimed = 0;
         if (tid == 0)
-            claimed = ticket ? (long)gridDim.x + (long)atomicAdd(ticket, 1ULL) : item + (long)gridDim.x;
+            claimed = ticket ? (long)gridDim.x + (long)(atomicAdd(ticket, 1ULL) - ticket_base) : item + (long)gridDim.x;
 
         // ---- phase 1: take this item's inputs (their TMA loads were issued one item ago, so the
         //      copy engine served them long before they are needed)
@@ -284,10 +287,15 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         //      (shared memory through constant offsets, D^T through the read-only path), the zero
         //      stream is issued while those loads fly, and the column pointer is carried from
         //      iteration to iteration instead of being rebuilt from (instance, column) per store.
-        {
+        auto columns = [&](auto packed_tag) {
+            constexpr bool PACKED = decltype(packed_tag)::value;
             constexpr int NRA = NR > 0 ? NR : 1;
-            double* gdst = J + (size_t)b * n * (size_t)M + (size_t)(jlo + warp) * (size_t)M;
-            const size_t gstep = (size_t)nwarps * (size_t)M;
+            // dense: J[b, j, :] of the first column of this warp; packed: the instance's values [nnz]
+            double* gdst = PACKED ? J + (size_t)b * (size_t)P.nnz
+                                  : J + (size_t)b * n * (size_t)M + (size_t)(jlo + warp) * (size_t)M;
+            const size_t gstep = PACKED ? 0 : (size_t)nwarps * (size_t)M;
+            const int* pm = PACKED ? P.pmap + (size_t)(jlo + warp) * (size_t)M : nullptr;   // row -> packed entry
+            const size_t pmstep = (size_t)nwarps * (size_t)M;
             int cur_key = -1, slot_sec = -1;
             double r_sdx[NRA], r_cf[NRA], r_sc[NRA];
             OgbSlot si = {0, 0, 0, 0};               // where this lane's output slot lands (per phase)
@@ -300,7 +308,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             const double* const s_coef = smem + pl.o_coef;
             const int4* const s_pcol = reinterpret_cast<const int4*>(smem + pl.o_pcol);
             const double* const s_sdx = W.sdx;       // (the input stage alternates between items)
-            for (int cc = warp; cc < ncols; cc += nwarps, gdst += gstep) {
+            for (int cc = warp; cc < ncols; cc += nwarps, gdst += gstep, pm += (PACKED ? pmstep : 0)) {
                 asm volatile("" : "+l"(gdst));       // keep the column pointer in registers ...
                 __builtin_assume(__isGlobal(gdst));  // ... and its stores in the global space (STG, not ST)
                 // (A) operands
@@ -313,6 +321,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
 #pragma unroll
                 for (int r = 0; r < NRA; ++r) dtv[r] = 0.0;
                 int a = -1;
+                int pos_blk = 0, pos_slot = -1;      // packed: entry of the state block's first row / of this lane's slot row
                 if (fcol) {
                     const OgbSec& S = ogb_sec(P, cd.sec);
                     dlt = s_pdlt[cc];
@@ -326,13 +335,16 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                             if (i < S.N) dtv[r] = __ldg(Dt + i);
                         }
                         dkk = __ldg(Dt + cd.k);
+                        // the N rows of state block a are consecutive entries of the column (row k is the
+                        // node row of slot a, the others are the D-block)
+                        if (PACKED) pos_blk = __ldg(pm + S.rdef + a * S.N);
                     }
                     if (lane < S.nouts) pv = s_pert[lane * W.G + cc];
                 }
                 // (B) zeros: 16-byte aligned body, an odd first / last double on its own
                 //     (with_fd == 2: structure probe -- only the overwrites below land, on a
                 //      sentinel-filled J; see ogb_jac_pattern.  3 / 4 / 5: timing probes)
-                if (with_fd != 2 && with_fd != 4) {
+                if (!PACKED && with_fd != 2 && with_fd != 4) {
                     const unsigned hj = (unsigned)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
                     const unsigned nbytes = ((unsigned)(M - hj) & ~1u) * 8u;
                     char* g = reinterpret_cast<char*>(gdst + hj) + lane * 16;
@@ -353,10 +365,9 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                     if (lane == 1 && ((M - hj) & 1)) gdst[M - 1] = 0.0;
                 }
                 __syncwarp();
-                if (with_fd >= 3) continue;          // timing probes: zero stream only / no column output
+                if (!PACKED && with_fd >= 3) continue;   // timing probes: zero stream only / no column output
                 // (C) the rows that can be non-zero
                 const int j = jlo + cc;
-                const OgbColOut col{gdst, gdst + meq, meq};
                 if (fcol) {
                     const OgbSec& S = ogb_sec(P, cd.sec);
                     const int N = S.N, k = cd.k;
@@ -364,6 +375,8 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                         slot_sec = cd.sec;
                         si = lane < S.nouts ? slots[S.out_off + lane] : OgbSlot{0, 0, 0, 0};
                     }
+                    const bool slot_hit = k >= si.klo && k < si.khi;
+                    if (PACKED && slot_hit) pos_slot = __ldg(pm + si.rbase + k);
                     if (a >= 0) {
                         const int key = cd.sec * 1024 + a;
                         if (key != cur_key) {                    // new state block: reload row constants
@@ -378,7 +391,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                                 }
                             }
                         }
-                        double* crow = gdst + (S.rdef + a * N + lane);
+                        double* crow = PACKED ? gdst + (pos_blk + lane) : gdst + (S.rdef + a * N + lane);
 #pragma unroll
                         for (int r = 0; r < NRA; ++r) {
                             const int i = lane + 32 * r;
@@ -388,7 +401,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                             }
                         }
                     }
-                    if (k >= si.klo && k < si.khi) {             // slot t = lane (slots 0..31)
+                    if (slot_hit) {                              // slot t = lane (slots 0..31)
                         double cp = pv;
                         const int r = si.rbase + k;
                         if (si.isdyn) {
@@ -396,7 +409,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                             if (lane == a) dxp = dxp + dkk * dlt;
                             cp = dxp - coef * cp;
                         }
-                        gdst[r] = ogb_fd_div(cp - s_sc[r], dx, rdx);
+                        gdst[PACKED ? pos_slot : r] = ogb_fd_div(cp - s_sc[r], dx, rdx);
                     }
                     for (int t = lane + 32; t < S.nouts; t += 32) {   // (rare) more than 32 output slots
                         const OgbSlot s2 = slots[S.out_off + t];
@@ -408,16 +421,27 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                                 if (t == a) dxp = dxp + dkk * dlt;
                                 cp = dxp - coef * cp;
                             }
-                            gdst[r] = ogb_fd_div(cp - s_sc[r], dx, rdx);
+                            gdst[PACKED ? __ldg(pm + r) : r] = ogb_fd_div(cp - s_sc[r], dx, rdx);
                         }
                     }
-                    if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots(P, W, j, W.px1[cc], dx, rdx, col, lane, 32);
-                    if (cd.pick >= 0 || P.has_running) ogb_scatter_scalar_cost(P, W, cd, cc, dx, rdx, col, lane, 32);
+                    if (PACKED) {
+                        const OgbColPacked col{gdst, pm};
+                        if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots(P, W, j, W.px1[cc], dx, rdx, col, lane, 32);
+                        if (cd.pick >= 0 || P.has_running) ogb_scatter_scalar_cost(P, W, cd, cc, dx, rdx, col, lane, 32);
+                    } else {
+                        const OgbColOut col{gdst, gdst + meq, meq};
+                        if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots(P, W, j, W.px1[cc], dx, rdx, col, lane, 32);
+                        if (cd.pick >= 0 || P.has_running) ogb_scatter_scalar_cost(P, W, cd, cc, dx, rdx, col, lane, 32);
+                    }
+                } else if (PACKED) {
+                    ogb_scatter_column(P, W, j, cc, OgbColPacked{gdst, pm}, lane, 32);
                 } else {
-                    ogb_scatter_column(P, W, j, cc, col, lane, 32);
+                    ogb_scatter_column(P, W, j, cc, OgbColOut{gdst, gdst + meq, meq}, lane, 32);
                 }
             }
-        }
+        };
+        if (with_fd == 6) columns(OgbBool<true>{});
+        else columns(OgbBool<false>{});
         __syncthreads();             // all warps are done reading this item's staging
         item = next_item;
     }

@@ -49,7 +49,6 @@ class DeviceProblem:
         self.ub = torch.as_tensor(np.asarray(ub, dtype=np.float64), device=self.device)
         self._work = None
         self._one = None
-        self.launches = 0                         # kernels launched through this handle
         self.fused_dx = False                     # ogb_eval / ogb_eval_fd = K1 + K2 (option 4 fuses them)
         mode = os.environ.get("OGB200_JIT", "")
         self.jit_error = None
@@ -73,9 +72,17 @@ class DeviceProblem:
             pass
 
     # ------------------------------------------------------------------ helpers
+    @property
+    def launches(self):
+        """Kernels launched through this handle so far, counted by the library where it launches them."""
+        info = capi.OgbProblemInfo()
+        self.b.problem_info_get(self.h, C.byref(info))
+        return int(info.launches)
+
     def set_option(self, key, value):
         """ogb_problem_set_option (include/ogb200.h): 0 generic columns, 1 threads, 2 jit,
-        3 grid cap, 4 fused D.X."""
+        3 grid cap, 4 fused D.X, 9 split pipeline (-1 auto / 0 fused / 1 split), 10 split chunk,
+        11 streaming zero stores in K2b."""
         self._rc(self.b.lib.ogb_problem_set_option(self.h, int(key), int(value)), "ogb_problem_set_option")
         if int(key) == 4:
             self.fused_dx = bool(value)
@@ -117,7 +124,6 @@ class DeviceProblem:
         with t.cuda.device(self.device):
             self._rc(self.b.lib.ogb_dx_gemm(self.h, P.data_ptr(), lb, ub, B, DX.data_ptr(), self._stream()),
                      "ogb_dx_gemm")
-        self.launches += 1
         return DX
 
     def sweep_fd(self, P, DX, out_c, out_J, abs_step=ABS_STEP):
@@ -128,7 +134,6 @@ class DeviceProblem:
             self._rc(self.b.lib.ogb_sweep(self.h, P.data_ptr(), DX.data_ptr(), self.lb.data_ptr(),
                                           self.ub.data_ptr(), float(abs_step), P.shape[0],
                                           out_c.data_ptr(), out_J.data_ptr(), self._stream()), "ogb_sweep")
-        self.launches += 1
         return out_c, out_J
 
     def eval(self, P, out=None):
@@ -140,7 +145,6 @@ class DeviceProblem:
         with t.cuda.device(self.device):
             self._rc(self.b.lib.ogb_eval(self.h, P.data_ptr(), B, c.data_ptr(), work.data_ptr(),
                                          self._stream()), "ogb_eval")
-        self.launches += 1 if self.fused_dx else 2
         return c
 
     def eval_fd(self, P, out_c=None, out_J=None, abs_step=ABS_STEP):
@@ -156,8 +160,40 @@ class DeviceProblem:
             self._rc(self.b.lib.ogb_eval_fd(self.h, P.data_ptr(), self.lb.data_ptr(), self.ub.data_ptr(),
                                             float(abs_step), B, c.data_ptr(), J.data_ptr(),
                                             work.data_ptr(), self._stream()), "ogb_eval_fd")
-        self.launches += 1 if self.fused_dx else 2
         return c, J
+
+    def eval_sparse(self, P, out_c=None, out_vals=None, abs_step=ABS_STEP):
+        """c (B, nrows) and the packed non-zeros of the FD Jacobian, vals (B, nnz) in the jac_pattern()
+        layout (ogb_eval_sparse: K1 + the sweep kernel with packed output; no dense J in HBM)."""
+        t = self.torch
+        P = self._check_P(P)
+        B = P.shape[0]
+        nnz = self.nnz
+        c = out_c if out_c is not None else t.empty((B, self.nrows), dtype=t.float64, device=self.device)
+        vals = out_vals if out_vals is not None else t.empty((B, nnz), dtype=t.float64, device=self.device)
+        assert c.is_contiguous() and vals.is_contiguous()
+        work = self._workspace(B)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_eval_sparse(self.h, P.data_ptr(), self.lb.data_ptr(), self.ub.data_ptr(),
+                                                float(abs_step), B, c.data_ptr(), vals.data_ptr(),
+                                                work.data_ptr(), self._stream()), "ogb_eval_sparse")
+        return c, vals
+
+    def densify(self, vals, out_J=None):
+        """K2b alone: packed values (B, nnz) -> dense J (B, nvars, nrows), zeros included."""
+        t = self.torch
+        B = vals.shape[0]
+        J = out_J if out_J is not None else t.empty((B, self.nvars, self.nrows), dtype=t.float64, device=self.device)
+        assert vals.is_contiguous() and J.is_contiguous() and vals.shape[1] == self.nnz
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_densify(self.h, vals.data_ptr(), B, J.data_ptr(), self._stream()), "ogb_densify")
+        return J
+
+    @property
+    def nnz(self):
+        if getattr(self, "_nnz", None) is None:
+            self._nnz = len(self.jac_pattern())
+        return self._nnz
 
     def host_evaluator(self):
         """numpy-in / numpy-out evaluator for sqp.slsqp_batch (one per engine: it owns a host session)."""
@@ -225,12 +261,10 @@ class DeviceProblem:
         """K3: dense device J (B, nvars, nrows) -> packed (B, nnz) device tensor."""
         t = self.torch
         B = J.shape[0]
-        nnz = len(self.jac_pattern()) if not hasattr(self, "_nnz") else self._nnz
-        self._nnz = nnz
+        nnz = self.nnz
         vals = out if out is not None else t.empty((B, nnz), dtype=t.float64, device=self.device)
         with t.cuda.device(self.device):
             self._rc(self.b.lib.ogb_pack(self.h, J.data_ptr(), B, vals.data_ptr(), self._stream()), "ogb_pack")
-        self.launches += 1
         return vals
 
     # ------------------------------------------------------------------ single-instance host API
@@ -320,9 +354,24 @@ class HostSession:
                                         float(abs_step), B, self._ptr(c, B * M), self._ptr(J, jcount),
                                         capi.HOST_MODES[mode])
         eng._rc(rc, "ogb_host_eval_fd")
-        st = self.stats()
-        eng.launches += st.launches
         return c, J
+
+    def eval_fd_scatter(self, P, c, C_ptrs, ld, mrows, G_ptrs=None, abs_step=ABS_STEP):
+        """ogb_host_eval_fd_scatter: the packed non-zeros of instance b go straight into the caller's
+        Fortran-ordered matrix at address C_ptrs[b] (leading dimension ld, rows < mrows) and the cost
+        row into the vector at G_ptrs[b] -- the SQP driver's persistent per-instance buffers (which
+        keep their zero background: only structural non-zeros are ever written)."""
+        eng = self.eng
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        B = int(P.shape[0])
+        n, M = eng.nvars, eng.nrows
+        assert len(C_ptrs) == B and (G_ptrs is None or len(G_ptrs) == B)
+        cp = (C.c_void_p * max(1, B))(*[int(a) for a in C_ptrs])
+        gp = (C.c_void_p * max(1, B))(*[int(a) for a in G_ptrs]) if G_ptrs is not None else None
+        rc = eng.b.lib.ogb_host_eval_fd_scatter(self.h, self._ptr(P, B * n), self.lb.ctypes.data, self.ub.ctypes.data,
+                                                float(abs_step), B, self._ptr(c, B * M), cp, int(ld), int(mrows), gp)
+        eng._rc(rc, "ogb_host_eval_fd_scatter")
+        return c
 
     def stats(self):
         st = capi.OgbHostStats()
@@ -350,11 +399,69 @@ class _HostEvaluator:
         array (e.g. a slice of the SQP driver's shared-memory block) that receives J."""
         X = np.ascontiguousarray(X, dtype=np.float64)
         k = X.shape[0]
+        self._session_for(k)
+        return self.session.eval_fd(X, J=out_J, mode="dense")
+
+    def eval_fd_scatter(self, X, C_ptrs, ld, mrows, G_ptrs=None):
+        """c (k, M); the Jacobians go straight into the SQP driver's per-instance matrices (see
+        HostSession.eval_fd_scatter): what sqp.slsqp_batch uses when the evaluator offers it."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        k = X.shape[0]
+        self._session_for(k)
+        c = np.empty((k, self.eng.nrows), dtype=np.float64)
+        return self.session.eval_fd_scatter(X, c, C_ptrs, ld, mrows, G_ptrs)
+
+    def _session_for(self, k):
         if self.session is None or self.session.max_batch < k:
             if self.session is not None:
                 self.session.close()
             self.session = self.eng.host_session(max(k, 16))
-        return self.session.eval_fd(X, J=out_J, mode="dense")
+
+
+def scipy_callables(eng, on_x=None, cost_derivative=None, args=()):
+    """(fun, constraints, jac) for scipy.optimize.minimize(method='SLSQP') whose values AND Jacobians
+    come from the device engine `eng` (anything with eval_host(x) -> c and eval_fd_host(x) -> c, J):
+    the replacement of the reference's `for_solver(cost_add / equality_add / inequality)` closures and of
+    SciPy's FD `cjac` (reference optimize.py:711-733, scipy/optimize/_slsqp_py.py:353-367).  One device
+    evaluation serves every callable asked at the same x (SLSQP asks fun, eq, ineq -- then jac, eq.jac,
+    ineq.jac -- at one point).  on_x(x): called with every x SciPy hands over (the facade keeps
+    prob.p = x like the reference); cost_derivative(x): optional user gradient of the cost."""
+    meq, mineq, M = eng.meq, eng.mineq, eng.nrows
+    memo = {"cx": None, "c": None, "jx": None, "jc": None, "J": None}
+    on_x = on_x or (lambda x: None)
+
+    def c_at(x):
+        on_x(x)
+        if memo["jx"] is not None and np.array_equal(memo["jx"], x):
+            return memo["jc"]
+        if memo["cx"] is None or not np.array_equal(memo["cx"], x):
+            memo["c"] = eng.eval_host(x)
+            memo["cx"] = np.array(x, copy=True)
+        return memo["c"]
+
+    def j_at(x):
+        on_x(x)
+        if memo["jx"] is None or not np.array_equal(memo["jx"], x):
+            memo["jc"], memo["J"] = eng.eval_fd_host(x)
+            memo["jx"] = np.array(x, copy=True)
+        return memo["J"]
+
+    def fun(x, *a):
+        return float(c_at(x)[M - 1])
+
+    cons = ({"type": "eq", "fun": lambda x, *a: c_at(x)[:meq],
+             "jac": lambda x, *a: j_at(x)[:, :meq].T, "args": args},
+            {"type": "ineq", "fun": lambda x, *a: c_at(x)[meq:meq + mineq],
+             "jac": lambda x, *a: j_at(x)[:, meq:meq + mineq].T, "args": args})
+    if cost_derivative is None:
+        # contiguous copy: SciPy 1.18's low-level SLSQP step reads a strided gradient as if it were
+        # contiguous (checked in tests/test_sqp.py), and J[:, M-1] is a strided column
+        jac = lambda x, *a: np.ascontiguousarray(j_at(x)[:, M - 1])
+    else:
+        def jac(x, *a):
+            on_x(x)
+            return cost_derivative(x)
+    return fun, cons, jac
 
 
 def lgl_device(N, device="cuda:0"):

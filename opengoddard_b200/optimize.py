@@ -31,6 +31,40 @@ def _plt():
     return plt
 
 
+def _lgl(capi, N):
+    """tau, w, D of the N-point LGL rule (reference optimize.py:183-213) for the constructor
+    attributes: libogb200's host entry point (the code the device kernel runs).  Only under the
+    explicit host backend ($OGB200_BACKEND=host: BASELINE configs[0], "plumbing, no GPU") a
+    missing library is replaced by the same Newton iteration in numpy; the cuda backend has no
+    fallback and raises."""
+    try:
+        return capi.lgl_host(N)
+    except (capi.OgbError, OSError):
+        if os.environ.get("OGB200_BACKEND") != "host":
+            raise
+    n = N - 1
+    x = -np.cos(np.pi * np.arange(N) / n)
+    P = np.zeros((N, N))
+    for _ in range(100):                          # Newton on (1 - x^2) P'_n(x) with the recurrence
+        P[:, 0], P[:, 1] = 1.0, x
+        for k in range(2, N):
+            P[:, k] = ((2 * k - 1) * x * P[:, k - 1] - (k - 1) * P[:, k - 2]) / k
+        step = (x * P[:, n] - P[:, n - 1]) / (N * P[:, n])
+        x = x - step
+        if np.abs(step).max() < 1e-16:
+            break
+    x[0], x[-1] = -1.0, 1.0
+    if N % 2:
+        x[n // 2] = 0.0
+    Pn = P[:, n]
+    w = 2.0 / (N * n * Pn ** 2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        D = Pn[:, None] / Pn[None, :] / (x[:, None] - x[None, :])
+    D[np.arange(N), np.arange(N)] = 0.0
+    D[0, 0], D[-1, -1] = -N * n / 4.0, N * n / 4.0
+    return x, w, D
+
+
 class Problem:
     """OpenGoddard Problem (reference optimize.py:38-880).
 
@@ -73,7 +107,7 @@ class Problem:
         self.number_of_variables = int(sum(self.number_of_param * nodes)) + self.number_of_section
         self.tau, self.w, self.D, self.time = [], [], [], []
         for i, N in enumerate(nodes):
-            tau, w, D = capi.lgl_host(N)          # same code the device kernel runs
+            tau, w, D = _lgl(capi, N)
             self.tau.append(tau)
             self.w.append(w)
             self.D.append(D)
@@ -107,6 +141,7 @@ class Problem:
         self.backend = None          # None -> $OGB200_BACKEND -> "cuda"
         self.device = None           # torch device for the cuda backend (default cuda:0)
         self._engine = None
+        self._engine_key = None
 
     # ------------------------------------------------------------------ layout
     def _span_state(self, state, section):
@@ -318,14 +353,52 @@ class Problem:
         self._check_callbacks()
         ir = tape.build_ir(self, obj)
         self._engine = engine.DeviceProblem(ir, self.bounds_arrays(), device or self.device, jit=jit)
+        self._engine_key = self._fingerprint(obj, jit)
         return self._engine
+
+    def _fingerprint(self, obj, jit):
+        """Everything a compiled engine has baked in: the callbacks, the constants they read from
+        `obj`, bounds (clipping and FD-step flipping happen on the device), units, knot flags, the
+        layout and the kernel flavour.  `_engine_for` recompiles when it changes."""
+        def freeze(v, depth=0):
+            if isinstance(v, (bool, int, float, complex, str, bytes, type(None))):
+                return ("v", repr(v))
+            if isinstance(v, np.generic):
+                return ("v", repr(v.item()))
+            if isinstance(v, np.ndarray):
+                return ("a", v.dtype.str, v.shape, v.tobytes())
+            if isinstance(v, (list, tuple)) and depth < 4:
+                return ("l",) + tuple(freeze(e, depth + 1) for e in v)
+            if isinstance(v, dict) and depth < 4:
+                return ("d",) + tuple((repr(k), freeze(e, depth + 1)) for k, e in sorted(v.items(), key=lambda kv: repr(kv[0])))
+            return ("id", id(v))
+        try:
+            attrs = tuple((k, freeze(v)) for k, v in sorted(vars(obj).items()))
+        except TypeError:
+            attrs = ()
+        lb, ub = self.bounds_arrays()
+        cbs = tuple(id(f) for f in list(self.dynamics) + [self.cost, self.running_cost, self.equality,
+                                                          self.inequality])
+        return (id(obj), attrs, lb.tobytes(), ub.tobytes(), freeze(self.unit_states), freeze(self.unit_controls),
+                float(self.unit_time), float(self.t0), freeze(list(self.knot_states_smooth)), tuple(self.nodes),
+                tuple(self.number_of_states), tuple(self.number_of_controls), cbs, bool(jit))
+
+    def _engine_for(self, obj, jit=True, device=None):
+        """The cached engine if it was compiled for exactly this problem state, else a fresh one."""
+        device = device or self.device
+        if self._engine is not None and (device is None or str(self._engine.device) == str(device)) and \
+                (obj is None or self._engine_key == self._fingerprint(obj, jit)):
+            return self._engine
+        if obj is None:
+            raise ValueError("no compiled engine yet: pass `obj`")
+        return self.compile(obj, device=device, jit=jit)
 
     def evaluate_batch(self, P, obj=None, jacobian=True, host=False):
         """Batched hot path: P (B, nvars) -> c (B, m+1) [, J (B, nvars, m+1)] as torch CUDA
         tensors; row m carries cost / grad cost.  J[b, j, :] is column j.  host=True: P is a host
         array and the results come back as numpy arrays in host memory through the host-buffer
         session (ogb_host_eval_fd: packed device->host transport, dense J rebuilt by host threads)."""
-        eng = self._engine if self._engine is not None else self.compile(obj)
+        eng = self._engine_for(obj)
         if host:
             ev = eng.host_evaluator()
             return ev.eval_fd(np.asarray(P, dtype=np.float64)) if jacobian else ev.eval(np.asarray(P, dtype=np.float64))
@@ -348,7 +421,7 @@ class Problem:
         the cores; sqp._ProcessStepper).  Returns dict(x, fun, status, nit, outer)."""
         from . import batch, sqp
         self._check_callbacks()
-        eng = self._engine if self._engine is not None else self.compile(obj)
+        eng = self._engine_for(obj)
         P0 = np.array(np.atleast_2d(P0), dtype=np.float64)
         return batch.run_sharded(
             lambda rows: self._solve_rows(eng, rows, obj, ftol, maxiter, max_outer, threads, sqp, processes),
@@ -415,42 +488,17 @@ class Problem:
 
     def _device_callables(self, obj):
         """SciPy-facing closures whose values AND Jacobians come from the CUDA kernels."""
-        eng = self.compile(obj, jit=False)       # one instance per call: latency-bound, skip NVRTC
-        meq, mineq, M = eng.meq, eng.mineq, eng.nrows
-        memo = {"cx": None, "c": None, "jx": None, "jc": None, "J": None}
-
-        def c_at(x):
-            self.p = x                                    # reference for_solver, :713
-            if memo["jx"] is not None and np.array_equal(memo["jx"], x):
-                return memo["jc"]
-            if memo["cx"] is None or not np.array_equal(memo["cx"], x):
-                memo["c"] = eng.eval_host(x)
-                memo["cx"] = np.array(x, copy=True)
-            return memo["c"]
-
-        def j_at(x):
-            self.p = x
-            if memo["jx"] is None or not np.array_equal(memo["jx"], x):
-                memo["jc"], memo["J"] = eng.eval_fd_host(x)
-                memo["jx"] = np.array(x, copy=True)
-            return memo["J"]
-
-        def fun(x, *a):
-            return float(c_at(x)[M - 1])
-
-        cons = ({"type": "eq", "fun": lambda x, *a: c_at(x)[:meq],
-                 "jac": lambda x, *a: j_at(x)[:, :meq].T, "args": (self, obj)},
-                {"type": "ineq", "fun": lambda x, *a: c_at(x)[meq:meq + mineq],
-                 "jac": lambda x, *a: j_at(x)[:, meq:meq + mineq].T, "args": (self, obj)})
-        if self.cost_derivative is None:
-            # contiguous copy: SciPy 1.18's low-level SLSQP step reads a strided gradient as if it
-            # were contiguous (checked in tests/test_sqp.py), and J[:, M-1] is a strided column
-            jac = lambda x, *a: np.ascontiguousarray(j_at(x)[:, M - 1])
-        else:
-            def jac(x, *a):                               # user gradient, host (reference :733)
+        from . import engine
+        eng = self._engine_for(obj, jit=False)   # one instance per call: latency-bound, skip NVRTC
+        grad = None
+        if self.cost_derivative is not None:
+            def grad(x):                                  # user gradient, host (reference :733)
                 self.p = x
                 return self.cost_derivative(self, obj)
-        return fun, cons, jac
+
+        def on_x(x):
+            self.p = x                                    # reference for_solver, :713
+        return engine.scipy_callables(eng, on_x=on_x, cost_derivative=grad, args=(self, obj))
 
     def _host_callables(self, obj):
         """Explicit opt-in numpy path (BASELINE.json configs[0]): the reference's closures."""

@@ -28,7 +28,24 @@ EXIT_MODES = {-1: "Gradient evaluation required (g & a)", 0: "Optimization termi
               8: "Positive directional derivative for linesearch", 9: "Iteration limit reached"}
 
 
+TESTED_SCIPY = ((1, 16), (1, 19))      # [lo, hi): releases whose private `_slsqplib.slsqp` calling convention
+#                                        (state dict, workspace sizing of _slsqp_py.py:453-520) this file mirrors
+
+
 def _low_level():
+    """SciPy's one-step SLSQP entry point.  It is private API: the state-dict keys, the workspace
+    formula in _Instance and the NaN-means-unbounded convention are copied from SciPy's own driver,
+    so an untested SciPy release is refused (a changed workspace layout would overflow the C core's
+    buffers) unless $OGB200_ALLOW_UNTESTED_SCIPY=1; tests/test_sqp.py checks a batch of one against
+    `minimize(method='SLSQP')` bit for bit on the installed SciPy."""
+    import os
+    import scipy
+    ver = tuple(int(t) for t in scipy.__version__.split(".")[:2] if t.isdigit())
+    if not (TESTED_SCIPY[0] <= ver < TESTED_SCIPY[1]) and os.environ.get("OGB200_ALLOW_UNTESTED_SCIPY") != "1":
+        raise NotImplementedError("the batched SQP driver mirrors the private SLSQP step of SciPy %d.%d-%d.%d; "
+                                  "installed: %s (set OGB200_ALLOW_UNTESTED_SCIPY=1 after running "
+                                  "tests/test_sqp.py)" % (TESTED_SCIPY[0] + (TESTED_SCIPY[1][0], TESTED_SCIPY[1][1] - 1)
+                                                          + (scipy.__version__,)))
     try:
         from scipy.optimize._slsqplib import slsqp
         from scipy.linalg.lapack import HAS_ILP64
@@ -41,7 +58,7 @@ def _low_level():
 class _Instance:
     """SLSQP state of one problem instance (mirrors scipy/optimize/_slsqp_py.py:453-520)."""
 
-    def __init__(self, x0, n, m, meq, acc, maxiter, int_dtype):
+    def __init__(self, x0, n, m, meq, acc, maxiter, int_dtype, C=None, g=None):
         mieq = m - meq
         self.x = np.array(x0, dtype=np.float64)
         self.state = {"acc": acc, "alpha": 0.0, "f0": 0.0, "gs": 0.0, "h1": 0.0, "h2": 0.0, "h3": 0.0,
@@ -55,9 +72,11 @@ class _Instance:
             size += 2 * n * (n + 1)
         self.buffer = np.zeros(max(size, 1), dtype=np.float64)
         self.mult = np.zeros([max(1, m + 2 * n + 2)], dtype=np.float64)
-        self.C = np.zeros([max(1, m), n], dtype=np.float64, order="F")
+        # the constraint normals SLSQP reads (scipy/optimize/_slsqp_py.py:517); its core never writes them,
+        # so the zero background survives and an evaluator may rewrite only the structural non-zeros
+        self.C = C if C is not None else np.zeros([max(1, m), n], dtype=np.float64, order="F")
         self.d = np.zeros([max(1, m)], dtype=np.float64)
-        self.g = np.zeros(n, dtype=np.float64)
+        self.g = g if g is not None else np.zeros(n, dtype=np.float64)
         self.fx = 0.0
         self.nfev = self.njev = 0
 
@@ -96,6 +115,17 @@ class _LocalStepper:
 
     def normals_buffer(self, ids):
         return None                  # (the per-instance C matrices are filled from the evaluator's array)
+
+    def normals_targets(self, ids):
+        """Addresses of the instances' own C matrices (Fortran order, leading dimension max(1, m)) and
+        gradient vectors, for an evaluator that scatters the Jacobian's non-zeros straight into them."""
+        return ([self.inst[b].C.ctypes.data for b in ids], [self.inst[b].g.ctypes.data for b in ids],
+                max(1, self.m))
+
+    def normals_written(self, ids, G):
+        if G is not None:
+            for k, b in enumerate(ids):
+                self.inst[b].g[:] = G[k]
 
     def step(self, active):
         if self.pool is not None:
@@ -154,23 +184,21 @@ def _worker_loop(conn):
                     pass
                 for k in names:
                     arr[k] = np.ndarray(shapes[k][0], dtype=shapes[k][1], buffer=shms[k].buf)
-                for b in owned:
-                    inst[b] = _Instance(arr["X"][b], n, m, meq, acc, maxiter, np.int64 if ilp64 else np.int32)
+                for b in owned:       # C and g live in the parent's shared memory: nothing is copied per step
+                    Cb = arr["C"][b].T if m > 0 else None              # (n, m) C-order block = (m, n) Fortran matrix
+                    inst[b] = _Instance(arr["X"][b], n, m, meq, acc, maxiter, np.int64 if ilp64 else np.int32,
+                                        C=Cb, g=arr["G"][b])
                 conn.send("ready")
                 continue
             if msg[0] == "release":
                 release()
                 conn.send("released")
                 continue
-            _, vals, norms, use_g, active = msg
+            _, vals, active = msg
             for b in vals:
                 it = inst[b]
                 it.fx = float(arr["D"][b, m])
                 it.d[:m] = arr["D"][b, :m]
-            for b in norms:
-                it = inst[b]
-                it.C[:m, :] = arr["J"][b, :, :m].T
-                it.g[:] = arr["G"][b] if use_g else arr["J"][b, :, m]
             for b in active:
                 it = inst[b]
                 slsqp(it.state, it.fx, it.g, it.C, it.d, it.x, it.mult, xl, xu, it.buffer, it.indices)
@@ -268,11 +296,13 @@ class _ProcessStepper:
         B = len(X0)
         self.m, self.B, self.pool, self.own_pool = m, B, pool, own_pool
         self.W = min(pool.W, B)
-        shapes = {"X": ((B, n), np.float64), "D": ((B, m + 1), np.float64), "J": ((B, n, m + 1), np.float64),
+        # "C": per instance the (m, n) Fortran-ordered constraint normals SLSQP reads, i.e. an (n, m)
+        # C-ordered block; "G": the cost gradients.  The workers' SLSQP states use these blocks in place.
+        shapes = {"X": ((B, n), np.float64), "D": ((B, m + 1), np.float64), "C": ((B, n, max(1, m)), np.float64),
                   "G": ((B, n), np.float64), "mode": ((B,), np.int64), "iter": ((B,), np.int64),
                   "fx": ((B,), np.float64)}
         self.shms, self.arr = {}, {}
-        self._vals, self._norms, self._use_g = [], [], False
+        self._vals = []
         try:
             for k, (shape, dt) in shapes.items():
                 nbytes = max(8, int(np.prod(shape)) * np.dtype(dt).itemsize)
@@ -294,29 +324,33 @@ class _ProcessStepper:
         self._vals = list(ids)
 
     def normals_buffer(self, ids):
-        """The shared-memory block that will hold the Jacobians of `ids`, if they are one contiguous run
-        of instances: the evaluator then writes them there itself (no copy through this process)."""
-        if len(ids) and ids[-1] - ids[0] + 1 == len(ids):
-            return self.arr["J"][ids[0]:ids[-1] + 1]
         return None
 
-    def put_normals(self, ids, J, G):
-        idx = np.asarray(ids, dtype=np.int64)
-        if not (isinstance(J, np.ndarray) and J.base is not None and np.shares_memory(J, self.arr["J"])):
-            self.arr["J"][idx] = J
-        self._use_g = G is not None
+    def normals_targets(self, ids):
+        """Addresses of the instances' C blocks / gradient rows in shared memory (see _LocalStepper)."""
+        C0, G0 = self.arr["C"].ctypes.data, self.arr["G"].ctypes.data
+        cs, gs = self.arr["C"].strides[0], self.arr["G"].strides[0]
+        return [C0 + b * cs for b in ids], [G0 + b * gs for b in ids], max(1, self.m)
+
+    def normals_written(self, ids, G):
         if G is not None:
-            self.arr["G"][idx] = G
-        self._norms = list(ids)
+            self.arr["G"][np.asarray(ids, dtype=np.int64)] = G
+
+    def put_normals(self, ids, J, G):
+        m = self.m
+        idx = np.asarray(ids, dtype=np.int64)
+        if m > 0:
+            self.arr["C"][idx] = J[:, :, :m]
+        self.arr["G"][idx] = G if G is not None else J[:, :, m]
 
     def step(self, active):
         W = self.W
         for w in range(W):
             pick = lambda ids: [b for b in ids if b % W == w]
-            self.pool.conns[w].send(("step", pick(self._vals), pick(self._norms), self._use_g, pick(active)))
+            self.pool.conns[w].send(("step", pick(self._vals), pick(active)))
         for w in range(W):
             self.pool.wait(w, "done")
-        self._vals, self._norms = [], []
+        self._vals = []
 
     def x(self, b):
         return self.arr["X"][b]
@@ -392,12 +426,24 @@ def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_g
     try:
         # mode 0 on entry: objective, constraints and gradients at the start point
         ids = list(range(B))
-        direct = bool(getattr(evaluator, "accepts_out", False))
-        buf = st.normals_buffer(ids) if direct else None
-        X_all = np.stack([st.x(b) for b in ids])
-        c, J = evaluator.eval_fd(X_all, out_J=buf) if buf is not None else evaluator.eval_fd(X_all)
-        st.put_values(ids, c)
-        st.put_normals(ids, J, grads(ids))
+        scatter = getattr(evaluator, "eval_fd_scatter", None)
+
+        def normals(ids):
+            """constraint values + Jacobians of the instances `ids` at their current x, into the SLSQP states:
+            scattered by the evaluator straight into the instances' C / g buffers when it can, else copied
+            from its dense (k, n, m + 1) array"""
+            X = np.stack([st.x(b) for b in ids])
+            G = grads(ids)
+            if scatter is not None:
+                Cp, Gp, ld = st.normals_targets(ids)
+                c = scatter(X, Cp, ld, m, Gp if G is None else None)
+                st.normals_written(ids, G)
+            else:
+                c, J = evaluator.eval_fd(X)
+                st.put_normals(ids, J, G)
+            return c
+
+        st.put_values(ids, normals(ids))
         nfev += 1
         njev += 1
         active = list(range(B))
@@ -413,10 +459,7 @@ def slsqp_batch(evaluator, X0, lb, ub, meq, mineq, ftol=1e-6, maxiter=25, cost_g
                 st.put_values(need_f, evaluator.eval(Xf))
                 nfev[need_f] += 1
             if need_g:
-                Xg = np.stack([st.x(b) for b in need_g])
-                buf = st.normals_buffer(need_g) if direct else None
-                _, Jg = evaluator.eval_fd(Xg, out_J=buf) if buf is not None else evaluator.eval_fd(Xg)
-                st.put_normals(need_g, Jg, grads(need_g))
+                normals(need_g)
                 njev[need_g] += 1
             if callback is not None:
                 for b in active:

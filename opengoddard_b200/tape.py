@@ -280,3 +280,49 @@ def _build_ir(prob, obj):
         node_tapes=node_tapes, scalar_tape=scalar_tape, nvars=ctx.nvars,
         tables=[{k: v for k, v in t.items() if k != "keep"} for t in ctx.tables],
         meta={"graph_nodes": len(g.nodes)})
+
+
+# ------------------------------------------------------------------ (de)serialisation
+def ir_to_arrays(ir):
+    """ProblemIR -> dict of numpy arrays (np.savez-able): a traced problem can be shipped without the
+    Python callbacks it came from (tests/golden/example_XX_ir.npz hold the traces of the reference's
+    shipped example scripts; engine.DeviceProblem(ir_from_arrays(...), bounds) rebuilds the engine)."""
+    out = {"layout": np.array([ir.nodes, ir.nstates, ir.ncontrols], dtype=np.int64),
+           "unit_states": np.array(ir.unit_states, dtype=np.float64),
+           "scalars": np.array([ir.unit_time, ir.t0], dtype=np.float64),
+           "flags": np.array([ir.meq_user, ir.mineq_user, int(ir.has_running_cost), ir.nvars, len(ir.tables)],
+                             dtype=np.int64),
+           "knot_smooth": np.array([1 if k else 0 for k in ir.knot_smooth], dtype=np.uint8)}
+    for name, tp in [("node%d" % s, t) for s, t in enumerate(ir.node_tapes)] + [("scalar", ir.scalar_tape)]:
+        out[name + "_code"] = np.asarray(tp.code, dtype=np.uint64)
+        out[name + "_consts"] = np.asarray(tp.consts, dtype=np.float64)
+        out[name + "_outs"] = np.array(tp.outs, dtype=np.int64).reshape(-1, 4)
+        out[name + "_nreg"] = np.array([tp.nreg], dtype=np.int64)
+    for i, t in enumerate(ir.tables):
+        out["table%d_x" % i] = np.asarray(t["x"], dtype=np.float64)
+        out["table%d_y" % i] = np.asarray(t["y"], dtype=np.float64)
+        out["table%d_meta" % i] = np.array([t["variant"], 1.0 if t["extrapolate"] else 0.0, t["fill_below"],
+                                            t["fill_above"]], dtype=np.float64)
+    return out
+
+
+def ir_from_arrays(d):
+    """Inverse of ir_to_arrays (d: a dict or an open .npz)."""
+    def tp(name):
+        return Tape(np.asarray(d[name + "_code"], dtype=np.uint64), np.asarray(d[name + "_consts"], dtype=np.float64),
+                    [tuple(int(v) for v in row) for row in np.asarray(d[name + "_outs"]).reshape(-1, 4)],
+                    int(d[name + "_nreg"][0]))
+    layout = np.asarray(d["layout"])
+    flags = [int(v) for v in d["flags"]]
+    tables = []
+    for i in range(flags[4]):
+        meta = np.asarray(d["table%d_meta" % i])
+        tables.append(dict(x=np.asarray(d["table%d_x" % i]), y=np.asarray(d["table%d_y" % i]), variant=int(meta[0]),
+                           extrapolate=bool(meta[1]), fill_below=float(meta[2]), fill_above=float(meta[3])))
+    nsec = layout.shape[1]
+    return ProblemIR(nodes=[int(v) for v in layout[0]], nstates=[int(v) for v in layout[1]],
+                     ncontrols=[int(v) for v in layout[2]], unit_states=[float(v) for v in d["unit_states"]],
+                     unit_time=float(d["scalars"][0]), t0=float(d["scalars"][1]),
+                     knot_smooth=[bool(v) for v in d["knot_smooth"]], meq_user=flags[0], mineq_user=flags[1],
+                     has_running_cost=bool(flags[2]), node_tapes=[tp("node%d" % s) for s in range(nsec)],
+                     scalar_tape=tp("scalar"), nvars=flags[3], tables=tables, meta={"loaded": True})

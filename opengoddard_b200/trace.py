@@ -672,11 +672,31 @@ class TraceView:
         object.__setattr__(self, "_prob", prob)
         object.__setattr__(self, "_ctx", ctx)
 
+    # Attributes of the real Problem a traced callback may read: layout, LGL data, units and the
+    # index helpers -- none of them depends on the decision vector.  Everything else the class
+    # defines (time_update, time_knots, to_csv, plot, solve, the setters ...) reads or writes prob.p
+    # and would bake the CURRENT decision vector into the tape as constants, so it is refused
+    # unless overridden below with a traced version.
+    _PASS = frozenset((
+        "nodes", "number_of_states", "number_of_controls", "number_of_section", "number_of_variables",
+        "number_of_param", "div", "tau", "w", "D", "time", "time_all_section", "time_init", "t0",
+        "unit_states", "unit_controls", "unit_time", "maxIterator", "iterator", "bounds",
+        "knot_states_smooth", "dynamics", "cost", "running_cost", "cost_derivative", "equality",
+        "inequality", "index_states", "index_controls", "index_time_final", "time_to_tau",
+        "_division_states", "_division_controls", "_span_state", "_span_control", "bounds_arrays",
+        "backend", "device"))
+
     def __getattr__(self, name):
         if name == "p":
             raise TraceError("direct access to prob.p inside a callback cannot be traced; "
                              "use prob.states()/controls()/time_final()")
-        return getattr(self._prob, name)
+        prob = self._prob
+        if name in self._PASS or (name in vars(prob) and not hasattr(type(prob), name)):
+            return getattr(prob, name)          # whitelisted, or an attribute the user attached
+        if hasattr(prob, name):
+            raise TraceError("prob.%s reads or writes the decision vector and cannot be used inside a "
+                             "callback that is compiled for the device" % name)
+        raise AttributeError(name)
 
     def __setattr__(self, name, value):
         raise TraceError("callbacks must not modify the Problem while being evaluated")
@@ -730,6 +750,10 @@ class TraceView:
 
     def time_final_all_section(self):
         return [self.time_final(s) for s in range(self._ctx.nsec)]
+
+    def time_knots(self):
+        # reference optimize.py:533-540 ([0] + final times; the reference assumes t0 = 0 here)
+        return [0] + self.time_final_all_section()
 
 
 class interp1d_tracing:

@@ -35,8 +35,11 @@ from oracle import ref_loader  # noqa: E402
 ABS_STEP = float(np.sqrt(np.finfo(np.float64).eps))   # scipy/optimize/_slsqp_py.py:34
 
 LGL_NODES = (3, 4, 5, 8, 20, 25, 30, 40, 50, 64, 100, 128)
-EXAMPLES_FD = ("01", "04", "05", "09", "10", "11")
-EXAMPLES_C = ("02", "03", "06", "07", "08")
+EXAMPLES_FD = ("01", "02", "03", "04", "05", "06", "07", "08", "09", "10", "11")
+EXAMPLES_C = ()
+# solve-level goldens: the reference's own SLSQP run (its closures, its FD Jacobians, SciPy's minimize
+# exactly as optimize.py:740-749 calls it) stopped after k major iterations, from the shipped guess
+EXAMPLES_SOLVE = {"01": (1, 2, 3, 6), "04": (1, 2, 3), "05": (1, 2, 3)}
 WORKLOAD_INSTANCES = {
     "cfg1_brachistochrone20": 3,
     "cfg2_goddard50": 4,
@@ -135,6 +138,51 @@ def golden_example(mod, tag, with_fd):
         out["J_eq"] = fd_jac(cap.constraints[0]["fun"], x, cap.constraints[0]["args"], lb, ub)
         out["J_ineq"] = fd_jac(cap.constraints[1]["fun"], x, cap.constraints[1]["args"], lb, ub)
         out["g_cost"] = fd_jac(cap.fun, x, cap.args, lb, ub).ravel()
+    if tag in EXAMPLES_SOLVE:
+        from scipy import optimize
+        ftol = (cap.options or {}).get("ftol", 1e-6)
+        out["solve_ftol"] = np.float64(ftol)
+
+        def run(k, cons=cap.constraints, start=x0):
+            with contextlib.redirect_stdout(io.StringIO()):
+                return optimize.minimize(cap.fun, np.array(start, dtype=float), args=cap.args, bounds=cap.bounds,
+                                         constraints=cons, jac=cap.jac, method="SLSQP",
+                                         options={"disp": False, "maxiter": k, "ftol": ftol})
+        for k in EXAMPLES_SOLVE[tag]:
+            opt = run(k)
+            out["solve_x_%d" % k] = np.array(opt.x, dtype=float)
+            out["solve_fun_%d" % k] = np.float64(opt.fun)
+            out["solve_status_%d" % k] = np.int64(opt.status)
+            out["solve_nit_%d" % k] = np.int64(opt.nit)
+        # the reference's c and FD Jacobians at its own last recorded iterate (a point reached by the
+        # optimiser: active bounds, non-smooth guesses gone) -- evaluation parity along the trajectory
+        k = EXAMPLES_SOLVE[tag][-1]
+        xk = np.clip(out["solve_x_%d" % k], lb, ub)
+        out["traj_k"] = np.int64(k)
+        out["traj_c_eq"] = np.atleast_1d(cap.eq(xk.copy())).astype(float)
+        out["traj_c_ineq"] = np.atleast_1d(cap.ineq(xk.copy())).astype(float)
+        out["traj_cost"] = np.float64(cap.cost(xk.copy()))
+        out["traj_J_eq"] = fd_jac(cap.constraints[0]["fun"], xk.copy(), cap.constraints[0]["args"], lb, ub)
+        out["traj_J_ineq"] = fd_jac(cap.constraints[1]["fun"], xk.copy(), cap.constraints[1]["args"], lb, ub)
+        out["traj_g_cost"] = fd_jac(cap.fun, xk.copy(), cap.args, lb, ub).ravel()
+        # how well-posed is "the iterate after k iterations"?  The reference's own first iterate when its FD
+        # Jacobians are perturbed by 1e-12 relative (seeded): SLSQP's LSQ step on these problems is
+        # discontinuous in its inputs, so iterate-level parity cannot be asserted (tests/test_examples_gpu.py)
+        rng = np.random.default_rng(20261017)
+        noisy = tuple(dict(c, jac=(lambda x, *a, c=c: (lambda J: J * (1.0 + 1e-12 * rng.standard_normal(J.shape)))(
+            fd_jac(c["fun"], x, a, lb, ub)))) for c in cap.constraints)
+        out["solve_x_1_perturbed_1e-12"] = np.array(run(1, cons=noisy).x, dtype=float)
+        if tag == "01":                              # converges: the reference's outer loop (optimize.py:738-755)
+            x, outer = np.array(x0, dtype=float), 0
+            for outer in range(1, 31):
+                opt = run(25, start=x)
+                x = opt.x
+                if opt.status == 0:
+                    break
+            out["solve_final_x"] = np.array(x, dtype=float)
+            out["solve_final_fun"] = np.float64(opt.fun)
+            out["solve_final_status"] = np.int64(opt.status)
+            out["solve_final_outer"] = np.int64(outer)
     np.savez_compressed(os.path.join(GOLD, "example_%s.npz" % tag), **out)
     print("example", tag, script, "n=%d meq=%d mineq=%d" % (x0.size, out["c_eq"].size,
                                                             out["c_ineq"].size))

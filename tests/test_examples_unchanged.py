@@ -8,59 +8,17 @@ emulation, tests/emu) must reproduce the c vector -- and for the BASELINE exampl
 FD Jacobian -- that the reference itself produced for that script (tests/golden/example_XX).  Example 11
 interpolates data tables (scipy interp1d) inside its dynamics: those become device lookup tables.
 Example 01 is additionally solved end to end on the explicit host backend."""
-import contextlib
-import io
 import os
-import sys
 
 import numpy as np
 import pytest
 
 from oracle import ref_loader
+from oracle.example_trace import run_script
 from tests.helpers import assert_c_close, assert_J_close, golden
 
 EXDIR = os.path.join(ref_loader.REFERENCE_ROOT, "examples")
 pytestmark = pytest.mark.skipif(not os.path.isdir(EXDIR), reason="reference examples only in the build container")
-
-
-def run_script(tag, intercept=True, env_backend=None):
-    import OpenGoddard.optimize as api
-    ref_loader.install_matplotlib_stub()
-    ref_loader.install_scipy_shims()
-    script = [f for f in sorted(os.listdir(EXDIR)) if f.startswith(tag) and f.endswith(".py")][0]
-    box = {}
-    real_solve = api.Problem.solve
-
-    def fake_solve(self, obj, display_func=None, **options):
-        box["prob"], box["obj"], box["options"] = self, obj, options
-
-    cwd = os.getcwd()
-    os.chdir(EXDIR)
-    if intercept:
-        api.Problem.solve = fake_solve
-    old = os.environ.get("OGB200_BACKEND")
-    if env_backend:
-        os.environ["OGB200_BACKEND"] = env_backend
-    out = io.StringIO()
-    try:
-        glb = {"__name__": "__main__", "__file__": script}
-        with contextlib.redirect_stdout(out):
-            try:
-                exec(compile(open(script).read(), script, "exec"), glb)
-            except Exception:
-                if intercept and "prob" in box:
-                    pass                      # post-processing on an unsolved problem may fail
-                else:
-                    raise
-    finally:
-        os.chdir(cwd)
-        api.Problem.solve = real_solve
-        if env_backend:
-            if old is None:
-                os.environ.pop("OGB200_BACKEND", None)
-            else:
-                os.environ["OGB200_BACKEND"] = old
-    return box, glb, out.getvalue()
 
 
 @pytest.mark.parametrize("tag", ["01", "02", "03", "04", "05", "06", "07", "08", "09", "10", "11"])

@@ -191,3 +191,78 @@ def test_example_c_vectors_under_the_facade(api):
         assert np.allclose(cons[0]["fun"](x.copy()), e["c_eq"], rtol=0, atol=1e-8)
         assert np.array_equal(cons[1]["fun"](x.copy()), e["c_ineq"])
         assert abs(fun(x.copy()) - e["cost"]) <= 1e-12 * max(1.0, abs(float(e["cost"])))   # LGL weights differ by ulps
+
+
+def test_traced_callbacks_cannot_bake_the_decision_vector_into_the_tape(api):
+    """TraceView forwards only attributes that do not depend on prob.p.  time_knots() is traced
+    (Sym values built from time_final), time_update() and the setters are refused -- previously they ran
+    against the real prob.p and their result became a tape constant, silently."""
+    wl = workloads.build("cfg3_goddard_knot30x2", api)
+    prob = wl.prob
+    ctx = trace.TraceContext(prob)
+    view = trace.TraceView(prob, ctx)
+    knots = view.time_knots()
+    assert knots[0] == 0 and all(isinstance(k, trace.Sym) for k in knots[1:]) and len(knots) == 3
+    for name in ("time_update", "set_states", "set_time_final", "to_csv", "plot", "solve", "evaluate_batch"):
+        with pytest.raises(trace.TraceError):
+            getattr(view, name)
+    assert view.nodes == prob.nodes and view.unit_time == prob.unit_time and view.index_time_final(0) == prob.index_time_final(0)
+    prob.my_table = [1.0, 2.0]                   # an attribute the user attached passes through
+    assert view.my_table == [1.0, 2.0]
+    with pytest.raises(AttributeError):
+        view.no_such_attribute
+
+    def ineq_with_time_update(p, obj):
+        t = p.time_update()
+        r = api.Condition()
+        r.lower_bound(p.states_all_section(0), t)
+        return r()
+    prob.inequality = ineq_with_time_update
+    with pytest.raises(trace.TraceError):
+        tape.build_ir(prob, wl.obj)
+
+
+def test_engine_cache_is_keyed_on_the_problem_state(api):
+    """evaluate_batch / solve_batch must not reuse an engine compiled for another obj,
+    other bounds, units, knot flags, callbacks or kernel flavour."""
+    wl = workloads.build("cfg2_goddard50", api)
+    prob, obj = wl.prob, wl.obj
+    base = prob._fingerprint(obj, True)
+    assert base == prob._fingerprint(obj, True)
+    assert base != prob._fingerprint(obj, False)                     # solve() compiles without NVRTC
+    name = next(k for k, v in vars(obj).items() if isinstance(v, float))
+    old = getattr(obj, name)
+    setattr(obj, name, old * 1.5)                                    # Monte-Carlo loop mutating obj in place
+    assert prob._fingerprint(obj, True) != base
+    setattr(obj, name, old)
+    assert prob._fingerprint(obj, True) == base
+    prob.set_states_bounds(0, 0, 0.5, 2.0)
+    changed = prob._fingerprint(obj, True)
+    assert changed != base
+    prob.set_unit_states(0, 0, 3.0)
+    assert prob._fingerprint(obj, True) != changed
+    compiled = []
+
+    class FakeEngine:
+        device = "cuda:0"
+    prob.compile = lambda o, device=None, jit=True: (compiled.append(jit), setattr(prob, "_engine", FakeEngine()),
+                                                     setattr(prob, "_engine_key", prob._fingerprint(o, jit)), prob._engine)[-1]
+    e1 = prob._engine_for(obj, jit=True)
+    assert prob._engine_for(obj, jit=True) is e1 and compiled == [True]
+    prob.set_states_bounds(1, 0, -1.0, 1.0)
+    assert prob._engine_for(obj, jit=True) is not e1 and compiled == [True, True]
+    prob._engine_for(obj, jit=False)
+    assert compiled == [True, True, False]
+    assert prob._engine_for(None) is prob._engine                    # no obj: whatever was compiled last
+
+
+def test_untested_scipy_is_refused(monkeypatch):
+    """the batched SQP driver mirrors private SciPy API; outside the tested releases it refuses."""
+    import scipy
+    from opengoddard_b200 import sqp
+    sqp._low_level()
+    monkeypatch.setattr(scipy, "__version__", "1.25.0")
+    with pytest.raises(NotImplementedError):
+        sqp._low_level()
+    monkeypatch.setenv("OGB200_ALLOW_UNTESTED_SCIPY", "1")
+    sqp._low_level()

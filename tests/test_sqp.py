@@ -150,39 +150,50 @@ def test_worker_pool_is_reusable_across_solves():
     assert pool.procs == []
 
 
-class OutEvaluator(OracleEvaluator):
-    """Like the device evaluator: can write the Jacobians into a buffer the driver hands it."""
-    accepts_out = True
+class ScatterEvaluator(OracleEvaluator):
+    """Like the device evaluator (engine._HostEvaluator.eval_fd_scatter): delivers the Jacobians straight
+    into the SQP driver's own per-instance buffers, addressed by raw pointers -- C_ptrs[k] a Fortran-ordered
+    (ld, n) matrix receiving the rows < mrows, G_ptrs[k] the gradient vector receiving the cost row."""
 
     def __init__(self, wl):
         super().__init__(wl)
         self.direct = 0
 
-    def eval_fd(self, X, out_J=None):
-        c, J = super().eval_fd(X)
-        if out_J is None:
-            return c, J
-        assert out_J.shape == J.shape and out_J.flags.c_contiguous
-        out_J[...] = J
+    def eval_fd_scatter(self, X, C_ptrs, ld, mrows, G_ptrs=None):
+        import ctypes
+        c, J = super().eval_fd(X)                      # J (k, n, m + 1)
+        n = J.shape[1]
+        for k in range(len(X)):
+            Cv = np.ctypeslib.as_array(ctypes.cast(int(C_ptrs[k]), ctypes.POINTER(ctypes.c_double)), shape=(n, ld))
+            Cv[:, :mrows] = J[k, :, :mrows]
+            if G_ptrs is not None:
+                gv = np.ctypeslib.as_array(ctypes.cast(int(G_ptrs[k]), ctypes.POINTER(ctypes.c_double)), shape=(n,))
+                gv[:] = J[k, :, -1]
         self.direct += 1
-        return c, out_J
+        return c
 
 
 def test_evaluator_writes_jacobians_straight_into_shared_memory():
-    """With worker processes and an evaluator that accepts a destination, a round in which a contiguous
-    run of instances asks for gradients has its Jacobians written into the shared block directly."""
+    """An evaluator that offers eval_fd_scatter writes the Jacobians into the SLSQP states' own buffers (the
+    workers' shared memory, or the local instances' C / g arrays): same iterates as the copying path."""
     from threadpoolctl import threadpool_limits
     wl = workloads.build("cfg1_brachistochrone20", og_numpy)
     meq, mineq = 64, 41
     P = workloads.make_batch(wl, 4)
-    ev1, ev2 = OracleEvaluator(wl), OutEvaluator(wl)
+    ev1, ev2 = OracleEvaluator(wl), ScatterEvaluator(wl)
     with threadpool_limits(1):
         one = sqp.slsqp_batch(ev1, P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5)
     two = sqp.slsqp_batch(ev2, P, ev2.lb, ev2.ub, meq, mineq, ftol=1e-6, maxiter=5, processes=2)
     assert ev2.direct >= 1
     for key in ("x", "fun", "status", "nit"):
         assert np.array_equal(one[key], two[key]), key
-    three = sqp.slsqp_batch(OutEvaluator(wl), P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5)   # local stepper
+    ev4 = ScatterEvaluator(wl)
     with threadpool_limits(1):
-        four = sqp.slsqp_batch(OutEvaluator(wl), P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5)
-    assert np.array_equal(four["x"], one["x"]) and three["x"].shape == one["x"].shape
+        four = sqp.slsqp_batch(ev4, P, ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=5)        # local stepper
+    assert ev4.direct >= 1 and np.array_equal(four["x"], one["x"])
+    # a user cost gradient takes precedence over the evaluator's cost row
+    grad = lambda x: og_numpy.eval_fd(wl.prob, wl.obj, x, ev1.lb, ev1.ub)[1][-1]
+    with threadpool_limits(1):
+        five = sqp.slsqp_batch(ScatterEvaluator(wl), P[:2], ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=3, cost_grad=grad)
+        six = sqp.slsqp_batch(OracleEvaluator(wl), P[:2], ev1.lb, ev1.ub, meq, mineq, ftol=1e-6, maxiter=3, cost_grad=grad)
+    assert np.array_equal(five["x"], six["x"])
