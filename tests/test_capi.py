@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     # sizes the C side static_asserts on are mirrored here: 4 x int32, pointer + int32 pairs
     assert ctypes.sizeof(capi.OgbOut) == 16
-    assert ctypes.sizeof(capi.OgbProblemInfo) == 44
+    assert ctypes.sizeof(capi.OgbProblemInfo) == 56          # 12 x int32 + int64 launches
     assert ctypes.sizeof(capi.OgbProgram) == 6 * 8 + 8 if False else ctypes.sizeof(capi.OgbProgram) % 8 == 0
 
 
