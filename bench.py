@@ -45,34 +45,81 @@ WORKLOADS = {                      # name -> (workloads.CONFIGS key, default bat
 }
 
 
-# ------------------------------------------------------------------ CPU baseline (oracle port)
-def _cpu_worker(args):
-    """Evaluate a slice of the sample with the numpy oracle; returns (n_done, seconds)."""
-    cfg, first, count = args
-    os.environ["OMP_NUM_THREADS"] = "1"
+# ------------------------------------------------------------------ CPU baseline (reference / oracle port)
+_CPU_STATE = {}
+
+
+def cpu_kind():
+    """"reference": the unmodified OpenGoddard module ($OPENGODDARD_REF, /root/reference or the copy
+    pip-installed into baseline/_ref) + SciPy's own approx_derivative; "port": the numpy oracle."""
+    if os.environ.get("OGB200_CPU_KIND") in ("reference", "port"):
+        return os.environ["OGB200_CPU_KIND"]
+    from oracle import ref_loader
+    return "reference" if ref_loader.reference_available() else "port"
+
+
+def _cpu_setup(cfg, kind):
+    key = (cfg, kind)
+    if key in _CPU_STATE:
+        return _CPU_STATE[key]
+    import numpy as np
     from opengoddard_b200 import workloads
-    from oracle import og_numpy
-    wl = workloads.build(cfg, og_numpy)
-    lb, ub = og_numpy.bounds_arrays(wl.prob)
+    if kind == "reference":
+        from scipy.optimize._numdiff import approx_derivative
+        from oracle import ref_loader
+        mod = ref_loader.load_reference()
+        wl = workloads.build(cfg, mod)
+        cap = ref_loader.capture_solve(mod, wl.prob, wl.obj)      # the closures Problem.solve hands to SciPy
+        lb = np.array([-np.inf if b[0] is None else float(b[0]) for b in cap.bounds])
+        ub = np.array([np.inf if b[1] is None else float(b[1]) for b in cap.bounds])
+        h = float(np.sqrt(np.finfo(np.float64).eps))
+        funs = [(cap.constraints[0]["fun"], cap.constraints[0]["args"]), (cap.constraints[1]["fun"], cap.constraints[1]["args"])]
+        if cap.jac is None:
+            funs.append((cap.fun, cap.args))                      # no cost_derivative: SciPy differences the cost too
+
+        def one(p):                                               # what SLSQP asks for in mode -1 (_slsqp_py.py:533-534)
+            x = np.clip(p, lb, ub)
+            for f, a in funs:
+                approx_derivative(f, x, method="2-point", abs_step=h, args=a, bounds=(lb, ub))
+    else:
+        from oracle import og_numpy
+        wl = workloads.build(cfg, og_numpy)
+        lb, ub = og_numpy.bounds_arrays(wl.prob)
+
+        def one(p):
+            og_numpy.eval_fd(wl.prob, wl.obj, p, lb, ub)
+    _CPU_STATE[key] = (wl, one)
+    return _CPU_STATE[key]
+
+
+def _cpu_worker(args):
+    """Evaluate a slice of the sample on one host core; returns (n_done, seconds)."""
+    cfg, first, count, kind = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import contextlib
+    import io
+    from opengoddard_b200 import workloads
+    with contextlib.redirect_stdout(io.StringIO()):
+        wl, one = _cpu_setup(cfg, kind)
     P = workloads.make_batch(wl, count, first=first)
     t0 = time.perf_counter()
     for p in P:
-        og_numpy.eval_fd(wl.prob, wl.obj, p, lb, ub)
+        one(p)
     return count, time.perf_counter() - t0
 
 
 class CpuPool:
-    """Host worker processes (spawned once) that run the oracle port on seeded instances."""
+    """Host worker processes (spawned once) that run the CPU path on seeded instances."""
 
-    def __init__(self, cfg, procs):
+    def __init__(self, cfg, procs, kind=None):
         import multiprocessing as mp
-        self.cfg, self.procs = cfg, procs
+        self.cfg, self.procs, self.kind = cfg, procs, kind or cpu_kind()
         self.pool = None
         if procs > 1:
             self.pool = mp.get_context("spawn").Pool(procs)
-            self.pool.map(_cpu_worker, [(cfg, 0, 1)] * procs)       # warm the workers (imports)
+            self.pool.map(_cpu_worker, [(cfg, 0, 1, self.kind)] * procs, chunksize=1)   # warm the workers (imports)
         else:
-            _cpu_worker((cfg, 0, 1))
+            _cpu_worker((cfg, 0, 1, self.kind))
 
     def run(self, sample, first=0):
         """-> (evals/s over the wall clock, wall seconds, summed CPU seconds)"""
@@ -80,7 +127,7 @@ class CpuPool:
         jobs = []
         for k in per:
             if k:
-                jobs.append((self.cfg, first, k))
+                jobs.append((self.cfg, first, k, self.kind))
                 first += k
         t0 = time.perf_counter()
         res = self.pool.map(_cpu_worker, jobs, chunksize=1) if self.pool else [_cpu_worker(j) for j in jobs]
@@ -183,14 +230,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm
+CPU_WHAT = {"reference": "the unmodified reference module (its Problem.solve closures) + SciPy approx_derivative for eq, "
+                         "ineq and cost",
+            "port": "oracle port: numpy callbacks + restated SciPy 2-point FD for eq, ineq and cost"}
+
+
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on every host core: each step evaluates a
+    bounded sample (8 seeded instances per worker) of the workload; value = best of the timed steps'
+    rates is NOT used -- the line reports total instances / total wall time like the CUDA arm."""
     if rank != 0:
         return
     cfg, _ = WORKLOADS[args.workload]
     procs = host_procs()
-    per_step = max(procs * 2, 32)                 # bounded sample per step
+    kind = cpu_kind()
+    per_step = procs * 8                          # >= 8 instances per worker per step: pool dispatch stays < 1 %
     vals = []
-    pool = CpuPool(cfg, procs)
+    pool = CpuPool(cfg, procs, kind)
     for _ in range(args.warmup):
         pool.run(per_step)
     for k in range(args.steps):
@@ -199,14 +255,15 @@ def run_reference(args, rank, world):
     pool.close()
     total_wall = sum(w for _, w in vals)
     value = per_step * len(vals) / total_wall
-    sample = "%d seeded instances of %s per step (oracle port, numpy + SciPy-restated FD), %d processes" % (
-        per_step, cfg, procs)
+    sample = "%d seeded instances of %s per step (%s), %d processes, 1 BLAS thread each" % (
+        per_step, cfg, CPU_WHAT[kind], procs)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_wall / len(vals),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": "%s_b%d" % (args.workload, args.batch), "sample_per_step": per_step},
-           "cpu_baseline": dict(value=value, unit=UNIT, cores=procs, kind="port", sample=sample, **cpu_info()),
+           "cpu_baseline": dict(value=value, unit=UNIT, cores=procs, kind=kind, sample=sample,
+                                best_step_value=max(v for v, _ in vals), **cpu_info()),
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -245,15 +302,15 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = host_procs()
+        kind = cpu_kind()
         sample = max(256, procs * 8)
-        pool = CpuPool(cfg, procs)
+        pool = CpuPool(cfg, procs, kind)
         v_all, wall_all, cpu_s = max(pool.run(sample) for _ in range(3))     # best of 3 (noisy shared hosts)
         pool.close()
-        v_one, _, _ = CpuPool(cfg, 1).run(48)
-        cpu = dict(value=v_all, unit=UNIT, cores=procs, kind="port",
-                   sample="%d seeded instances of %s (same generator as the GPU batch), oracle port: numpy "
-                          "callbacks + restated SciPy 2-point FD for eq, ineq and cost; best of 3 passes, %.1f s of CPU work each"
-                          % (sample, cfg, cpu_s),
+        v_one, _, _ = CpuPool(cfg, 1, kind).run(48)
+        cpu = dict(value=v_all, unit=UNIT, cores=procs, kind=kind,
+                   sample="%d seeded instances of %s (same generator as the GPU batch), %s; best of 3 passes, "
+                          "%.1f s of CPU work each" % (sample, cfg, CPU_WHAT[kind], cpu_s),
                    single_core_value=v_one, **cpu_info())
 
     import numpy as np

@@ -169,8 +169,9 @@ enum ogb_option {
                                     3 = zero stream only, 4 = no column output at all; 0 = normal             */
     OGB_OPT_SPLIT = 9,           /* how ogb_eval_fd produces the dense J: 0 = the fused sweep kernel (one launch after
                                     K1), 1 = the split pipeline (K1 -> K2a packed sweep on an internal stream, K2b
-                                    densify on the caller's stream, chunk by chunk), -1 (default) = split for batches
-                                    of >= 256 MB of dense J.  Results are bit-identical either way.                */
+                                    densify on the caller's stream, chunk by chunk), -1 (default) = automatic, which
+                                    currently means fused: it measured faster at every batch size (profiles/README.md).
+                                    Results are bit-identical either way.                                         */
     OGB_OPT_SPLIT_CHUNK = 10,    /* instances per chunk of the split pipeline (0 = auto, ~192 MB of dense J)        */
     OGB_OPT_DENSE_STREAMING = 11,/* 1 (default): K2b writes its zeros with st.global.cs (evict-first)              */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
@@ -183,6 +184,10 @@ int ogb_problem_set_option(void* prob, int key, int value);
  * without a GPU).  Returns the cubin size (> 0) and copies the generated source into `log`, or a
  * negative value and the compiler log.                                                      */
 int ogb_jit_check(const ogb_problem_desc* desc, char* log, int log_cap);
+/* ... the same for one of the three kernel variants: 0 = dense J / c only (what ogb_jit_check builds),
+ * 1 = packed FD output (ogb_eval_sparse), 2 = exact mode (ogb_eval_exact).  Each variant is compiled
+ * when it is first used.                                                                       */
+int ogb_jit_check_variant(const ogb_problem_desc* desc, int variant, char* log, int log_cap);
 
 /* Scratch the caller must provide to ogb_eval / ogb_eval_fd for a batch of B.     */
 size_t ogb_workspace_bytes(void* prob, int B);
@@ -226,6 +231,18 @@ int ogb_eval_fd(void* prob, const double* p, const double* lb, const double* ub,
 int ogb_eval_sparse(void* prob, const double* p, const double* lb, const double* ub, double abs_step,
                     int B, double* c, double* vals, void* work, void* stream);
 int ogb_densify(void* prob, const double* vals, int B, double* J, void* stream);
+
+/* ---- exact Jacobian mode (opt-in) ------------------------------------
+ * The same rows and columns with derivatives instead of difference quotients: the collocation block is
+ * analytic (D_p (x) I: d defect(a, i) / d x(a, k) = D[i, k]; reference optimize.py:677-696), everything that
+ * goes through a user callback is differentiated in forward mode -- the traced tapes run in dual
+ * arithmetic, one tangent per perturbed block -- at x = clip(p, lb, ub).  Output: c [B, nrows] (bit-identical
+ * to ogb_eval_fd's) and vals [B, nnz] in the ogb_jac_pattern layout (ogb_densify gives the dense matrix).
+ * This is NOT what the reference computes (SciPy's forward differences carry a truncation error of up to
+ * ~1e-5 of the row maximum and rounding noise of relative size 1 on small entries); it is what SLSQP would
+ * ideally be given.                                                                              */
+int ogb_eval_exact(void* prob, const double* p, const double* lb, const double* ub, int B, double* c,
+                   double* vals, void* work, void* stream);
 
 /* ---- packed Jacobian transport ---------------------------------------------------------
  * The FD Jacobian is structurally sparse: a perturbed state moves its own defect rows and the
@@ -271,6 +288,12 @@ void  ogb_host_session_destroy(void* session);
 int   ogb_host_eval_fd(void* session, const double* p_h, const double* lb_h, const double* ub_h,
                        double abs_step, int B, double* c_h, double* J_h, int mode);
 int   ogb_host_session_stats(void* session, ogb_host_stats* out);
+enum ogb_host_option {
+    OGB_HOST_OPT_EXACT = 0     /* 1: the session's Jacobians are the exact ones (ogb_eval_exact) instead of SciPy's
+                                  forward differences (ogb_eval_sparse); the packed modes only -- OGB_HOST_J_DMA
+                                  stays the FD Jacobian                                                          */
+};
+int   ogb_host_session_set_option(void* session, int key, int value);
 
 /* The same evaluation delivered straight into an SQP driver's own buffers -- what SciPy's
  * _eval_con_normals does per instance with `C[row:row+k, :] = jac(x)` (scipy/optimize/

@@ -168,6 +168,10 @@ def ogb():
         L.ogb_problem_set_option.argtypes = [vp, i32, i32]
         L.ogb_jit_check.restype = C.c_int
         L.ogb_jit_check.argtypes = [C.POINTER(OgbProblemDesc), C.c_char_p, C.c_int]
+        L.ogb_jit_check_variant.restype = C.c_int
+        L.ogb_jit_check_variant.argtypes = [C.POINTER(OgbProblemDesc), C.c_int, C.c_char_p, C.c_int]
+        L.ogb_eval_exact.restype = C.c_int
+        L.ogb_eval_exact.argtypes = [vp, dp, dp, dp, i32, dp, dp, vp, vp]
         L.ogb_workspace_bytes.restype = C.c_size_t
         L.ogb_workspace_bytes.argtypes = [vp, i32]
         L.ogb_dx_gemm.restype = C.c_int
@@ -194,6 +198,8 @@ def ogb():
         L.ogb_host_session_destroy.argtypes = [vp]
         L.ogb_host_eval_fd.restype = C.c_int
         L.ogb_host_eval_fd.argtypes = [vp, vp, vp, vp, C.c_double, i32, vp, vp, i32]
+        L.ogb_host_session_set_option.restype = C.c_int
+        L.ogb_host_session_set_option.argtypes = [vp, i32, i32]
         L.ogb_host_session_stats.restype = C.c_int
         L.ogb_host_session_stats.argtypes = [vp, C.POINTER(OgbHostStats)]
         L.ogb_host_expand.restype = C.c_int
@@ -235,13 +241,14 @@ def lgl_host(N):
     return tau, w, D
 
 
-def jit_check(ir):
-    """NVRTC-compile the specialised sweep kernel for a traced problem (no GPU needed).
-    Returns (cubin_bytes, generated_source); raises OgbError with the compiler log."""
+def jit_check(ir, variant=0):
+    """NVRTC-compile the specialised sweep kernel for a traced problem (no GPU needed); variant 0 = dense /
+    c only, 1 = packed FD output, 2 = exact mode.  Returns (cubin_bytes, generated_source); raises OgbError
+    with the compiler log."""
     b = ogb()
     desc, keep = make_desc(ir)
-    buf = C.create_string_buffer(1 << 20)
-    rc = b.lib.ogb_jit_check(C.byref(desc), buf, len(buf))
+    buf = C.create_string_buffer(1 << 21)
+    rc = b.lib.ogb_jit_check_variant(C.byref(desc), int(variant), buf, len(buf))
     if rc <= 0:
         raise OgbError("ogb_jit_check failed: " + b.error())
     return rc, buf.value.decode()

@@ -324,6 +324,145 @@ OGB_HD void ogb_run_tape(const OgbProb& P, const uint64_t* code, int ncode, cons
     }
 }
 
+// ------------------------------------------------------------------ exact derivatives (forward mode)
+// d/dx of ogb_interp: the slope of the segment the lookup used (0 where the table clamps or fills).
+OGB_HD double ogb_interp_slope(const OgbProb& P, int id, double x) {
+    const ogb_table T = P.tables[id];
+    const double* xp = P.tab_x + T.off;
+    const double* fp = P.tab_y + T.off;
+    const int n = T.len;
+    if (!T.extrapolate && (x < xp[0] || x > xp[n - 1])) return 0.0;
+    if (T.variant == 0) {
+        if (x > xp[n - 1] || x < xp[0] || !(x == x)) return 0.0;
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (xp[mid] <= x) lo = mid; else hi = mid - 1;
+        }
+        const int j = lo < n - 1 ? lo : n - 2;          // at a breakpoint: the segment to its right
+        return (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+    }
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (xp[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    const int i = lo < 1 ? 1 : (lo > n - 1 ? n - 1 : lo);
+    return (fp[i] - fp[i - 1]) / (xp[i] - xp[i - 1]);
+}
+
+// One instruction of a tape in dual arithmetic: value v (already computed from a, b, c the way
+// ogb_run_tape does) and tangents da, db, dc -> tangent of the result.
+OGB_HD double ogb_dual_rule(const OgbProb& P, int op, int tab, double v, double a, double b, double da, double db,
+                            double dc) {
+    // an operation none of whose operands moves has tangent 0 whatever its value: d sqrt(s) with s = x^2 at
+    // x = 0 is 0 / 0 by the chain rule, and 0 is the derivative (unary operations ignore field b)
+    const bool unary = (op >= OGB_NEG && op <= OGB_CEIL) || op == OGB_NOT || op == OGB_INTERP;
+    if (da == 0.0 && (unary || db == 0.0) && (op != OGB_SEL || dc == 0.0)) return 0.0;
+    switch (op) {
+        case OGB_ADD: return da + db;
+        case OGB_SUB: return da - db;
+        case OGB_MUL: return da * b + a * db;
+        case OGB_DIV: return (da - v * db) / b;
+        case OGB_POW: {
+            double d = 0.0;
+            if (da != 0.0) d = b * pow(a, b - 1.0) * da;
+            if (db != 0.0) d += v * log(a) * db;
+            return d;
+        }
+        case OGB_MIN: return (a < b || !(b == b)) ? da : db;       // fmin: a NaN operand loses
+        case OGB_MAX: return (a > b || !(b == b)) ? da : db;
+        case OGB_ATAN2: return (b * da - a * db) / (a * a + b * b);
+        case OGB_SEL: return a != 0.0 ? db : dc;
+        case OGB_NEG: return -da;
+        case OGB_SQRT: return da / (2.0 * v);
+        case OGB_EXP: return v * da;
+        case OGB_LOG: return da / a;
+        case OGB_SIN: return cos(a) * da;
+        case OGB_COS: return -sin(a) * da;
+        case OGB_TAN: return (1.0 + v * v) * da;
+        case OGB_ABS: return a > 0.0 ? da : (a < 0.0 ? -da : 0.0);
+        case OGB_SQUARE: return 2.0 * a * da;
+        case OGB_RECIP: return -(v * v) * da;
+        case OGB_ASIN: return da / sqrt(1.0 - a * a);
+        case OGB_ACOS: return -da / sqrt(1.0 - a * a);
+        case OGB_ATAN: return da / (1.0 + a * a);
+        case OGB_SINH: return cosh(a) * da;
+        case OGB_COSH: return sinh(a) * da;
+        case OGB_TANH: return (1.0 - v * v) * da;
+        case OGB_LOG10: return da / (a * 2.302585092994045684);
+        case OGB_INTERP: return ogb_interp_slope(P, tab, a) * da;
+        default: return 0.0;            // comparisons, logic, sign, floor, ceil: piecewise constant
+    }
+}
+
+// The tape in dual arithmetic: input `seed` carries tangent 1, every other input 0; output slot t
+// receives d(out_t)/d(input seed).  Same value arithmetic as ogb_run_tape.
+template <class Load>
+OGB_HD void ogb_run_tape_dual(const OgbProb& P, const uint64_t* code, int ncode, const double* consts,
+                              const Load& ld, int seed, double* out, int ostride) {
+    double r[OGB_MAX_REG], t[OGB_MAX_REG];
+    for (int pc = 0; pc < ncode; ++pc) {
+        const uint64_t ins = code[pc];
+        const int op = (int)(ins >> 56);
+        const int d = (int)((ins >> 42) & 0x3fff);
+        const int a = (int)((ins >> 28) & 0x3fff);
+        const int b = (int)((ins >> 14) & 0x3fff);
+        const int c = (int)(ins & 0x3fff);
+        double v;
+        switch (op) {
+            case OGB_LDP: r[d] = ld(a); t[d] = a == seed ? 1.0 : 0.0; continue;
+            case OGB_LDC: r[d] = consts[a]; t[d] = 0.0; continue;
+            case OGB_OUT: out[d * ostride] = t[a]; continue;
+            case OGB_NOP: continue;
+            case OGB_ADD: v = r[a] + r[b]; break;
+            case OGB_SUB: v = r[a] - r[b]; break;
+            case OGB_MUL: v = r[a] * r[b]; break;
+            case OGB_DIV: v = r[a] / r[b]; break;
+            case OGB_POW: v = pow(r[a], r[b]); break;
+            case OGB_MIN: v = fmin(r[a], r[b]); break;
+            case OGB_MAX: v = fmax(r[a], r[b]); break;
+            case OGB_ATAN2: v = atan2(r[a], r[b]); break;
+            case OGB_LT: v = r[a] < r[b] ? 1.0 : 0.0; break;
+            case OGB_LE: v = r[a] <= r[b] ? 1.0 : 0.0; break;
+            case OGB_GT: v = r[a] > r[b] ? 1.0 : 0.0; break;
+            case OGB_GE: v = r[a] >= r[b] ? 1.0 : 0.0; break;
+            case OGB_EQ: v = r[a] == r[b] ? 1.0 : 0.0; break;
+            case OGB_NE: v = r[a] != r[b] ? 1.0 : 0.0; break;
+            case OGB_SEL: v = r[a] != 0.0 ? r[b] : r[c]; break;
+            case OGB_NEG: v = -r[a]; break;
+            case OGB_SQRT: v = sqrt(r[a]); break;
+            case OGB_EXP: v = exp(r[a]); break;
+            case OGB_LOG: v = log(r[a]); break;
+            case OGB_SIN: v = sin(r[a]); break;
+            case OGB_COS: v = cos(r[a]); break;
+            case OGB_TAN: v = tan(r[a]); break;
+            case OGB_ABS: v = fabs(r[a]); break;
+            case OGB_SQUARE: v = r[a] * r[a]; break;
+            case OGB_RECIP: v = 1.0 / r[a]; break;
+            case OGB_ASIN: v = asin(r[a]); break;
+            case OGB_ACOS: v = acos(r[a]); break;
+            case OGB_ATAN: v = atan(r[a]); break;
+            case OGB_SINH: v = sinh(r[a]); break;
+            case OGB_COSH: v = cosh(r[a]); break;
+            case OGB_TANH: v = tanh(r[a]); break;
+            case OGB_LOG10: v = log10(r[a]); break;
+            case OGB_SIGN: v = (r[a] > 0.0) ? 1.0 : ((r[a] < 0.0) ? -1.0 : r[a]); break;
+            case OGB_FLOOR: v = floor(r[a]); break;
+            case OGB_CEIL: v = ceil(r[a]); break;
+            case OGB_AND: v = (r[a] != 0.0 && r[b] != 0.0) ? 1.0 : 0.0; break;
+            case OGB_OR: v = (r[a] != 0.0 || r[b] != 0.0) ? 1.0 : 0.0; break;
+            case OGB_NOT: v = (r[a] == 0.0) ? 1.0 : 0.0; break;
+            case OGB_INTERP: v = ogb_interp(P, b, r[a]); break;
+            default: continue;
+        }
+        // (SEL passes the tangents of its value operands b, c; INTERP's table id sits in field b)
+        const double tv = ogb_dual_rule(P, op, b, v, r[a], r[b], t[a], t[b], op == OGB_SEL ? t[c] : 0.0);
+        r[d] = v;
+        t[d] = tv;
+    }
+}
+
 // ------------------------------------------------------------------ helpers
 // a / dx, bit-identical to the IEEE division SciPy performs (_numdiff.py:711), from the
 // correctly rounded reciprocal rdx = 1/dx shared by the whole column: q = RN(a*rdx), exact
@@ -367,9 +506,19 @@ template <class Load>
 __device__ __forceinline__ void ogb_jit_node(const OgbProb& P, int sec, const Load& ld, double* out, int ostride);
 template <class Load>
 __device__ __forceinline__ void ogb_jit_scalar(const OgbProb& P, const Load& ld, double* out, int ostride);
+template <class Load>
+__device__ __forceinline__ void ogb_jit_node_dual(const OgbProb& P, int sec, const Load& ld, int seed, double* out, int ostride);
+template <class Load>
+__device__ __forceinline__ void ogb_jit_scalar_dual(const OgbProb& P, const Load& ld, int seed, double* out, int ostride);
 #define OGB_NODE_PROGRAM(s, S, ld, out, stride) ogb_jit_node(P, (s), (ld), (out), (stride))
 #define OGB_SCALAR_PROGRAM(ld, out, stride) ogb_jit_scalar(P, (ld), (out), (stride))
+#define OGB_NODE_PROGRAM_DUAL(s, S, ld, seed, out, stride) ogb_jit_node_dual(P, (s), (ld), (seed), (out), (stride))
+#define OGB_SCALAR_PROGRAM_DUAL(ld, seed, out, stride) ogb_jit_scalar_dual(P, (ld), (seed), (out), (stride))
 #else
+#define OGB_NODE_PROGRAM_DUAL(s, S, ld, seed, out, stride) \
+    ogb_run_tape_dual(P, P.code + (S).code_off, (S).ncode, P.consts + (S).const_off, (ld), (seed), (out), (stride))
+#define OGB_SCALAR_PROGRAM_DUAL(ld, seed, out, stride) \
+    ogb_run_tape_dual(P, P.code + P.sc_code_off, P.sc_ncode, P.consts + P.sc_const_off, (ld), (seed), (out), (stride))
 #define OGB_NODE_PROGRAM(s, S, ld, out, stride) \
     ogb_run_tape(P, P.code + (S).code_off, (S).ncode, P.consts + (S).const_off, (ld), (out), (stride))
 #define OGB_SCALAR_PROGRAM(ld, out, stride) \
@@ -631,4 +780,100 @@ OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl
         ogb_scatter_time(P, W, j, cd.blk, x1, dx, rdx, col, lane, nlanes);
     }
     ogb_scatter_scalar_cost(P, W, cd, cl, dx, rdx, col, lane, nlanes);
+}
+
+
+// ================================================================== exact Jacobian
+// The same rows and columns as the FD sweep, with derivatives instead of difference quotients:
+//   state column (s, a, k):  defect row (s, a, i) : D[i, k]                        (i != k)
+//                            defect row (s, b, k) : [b == a] D[k, k] - coef_s * d f_b / d x_a   at node k
+//                            point user row at k   : d row / d x_a;   knot rows: +1 / -u_post / u_prev
+//   control column          : the node rows only
+//   final-time column       : defect rows of its own phase: -f / 2, of the next phase: +f / 2
+//   scalar-program rows and the cost row: forward-mode tangent of the scalar tape (+ w * d running / d x)
+// (reference rows: optimize.py:670-709; (p * unit) / unit has derivative 1).  The tangents come from the
+// traced tapes run in dual arithmetic (ogb_run_tape_dual / the NVRTC-generated dual programs).
+
+// Job q of a work item in exact mode: q <= gtot as in ogb_job; q > gtot: tangents of column jlo + (q - gtot - 1)
+OGB_HD void ogb_job_exact(const OgbProb& P, const OgbWork& W, int q, int jlo) {
+    if (q <= P.gtot) { ogb_job(P, W, q, jlo, nullptr, nullptr, 0.0); return; }
+    const int cl = q - P.gtot - 1;
+    const int j = jlo + cl;
+    const OgbCol col = P.cols[j];
+    W.pcol[cl] = col;
+    if (col.sec >= 0) {
+        const OgbSec& S = ogb_sec(P, col.sec);
+        OgbNodeLoad ld{W.sp + S.off + col.k, S.N, -1, 0.0};
+        OGB_NODE_PROGRAM_DUAL(col.sec, S, ld, col.blk, W.pert + cl, W.G);
+    }
+    if (col.pick >= 0) {
+        OgbScalarLoad ld{W.sp, -1, 0.0};
+        OGB_SCALAR_PROGRAM_DUAL(ld, j, W.scpert + col.pick, P.npick);
+    }
+}
+
+// d cost / d x_j of column cl (one thread per column)
+OGB_HD void ogb_cost_column_exact(const OgbProb& P, const OgbWork& W, int cl) {
+    const OgbCol cd = W.pcol[cl];
+    if (!ogb_col_moves_cost(P, cd)) return;
+    double g = cd.pick >= 0 ? W.scpert[P.sc_cost_slot * P.npick + cd.pick] : 0.0;
+    if (P.has_running && cd.sec >= 0) {
+        const OgbSec& S = ogb_sec(P, cd.sec);
+        g = g + W.pert[S.run_slot * W.G + cl] * P.w[S.g0 + cd.k];
+    }
+    W.costp[cl] = g;
+}
+
+template <class Out>
+OGB_HD void ogb_scatter_column_exact(const OgbProb& P, const OgbWork& W, int j, int cl, const Out& col,
+                                     int lane, int nlanes) {
+    const OgbCol cd = W.pcol[cl];
+    if (cd.sec >= 0) {
+        const OgbSec& S = ogb_sec(P, cd.sec);
+        const int k = cd.k, a = cd.blk < S.ns ? cd.blk : -1;
+        const double coef = W.coef[3 * cd.sec];
+        if (a >= 0) {
+            const double* Dt = P.Dt + S.doff + k * S.N;            // column k of D
+            for (int i = lane; i < S.N; i += nlanes)
+                if (i != k) col.put(S.rdef + a * S.N + i, Dt[i]);
+        }
+        const int g = S.g0 + k;
+        for (int slot = lane; slot < S.nouts; slot += nlanes) {
+            const double t = W.pert[slot * W.G + cl];
+            if (slot < S.ns) {
+                const double dkk = slot == a ? P.D[S.doff + k * S.N + k] : 0.0;
+                col.put(S.rdef + slot * S.N + k, dkk - coef * t);
+            } else {
+                const ogb_out o = P.outs[S.out_off + slot];
+                if ((o.kind == OGB_OUT_EQ_POINT || o.kind == OGB_OUT_INEQ_POINT) && g >= o.glo && g < o.ghi)
+                    col.put(o.row + (g - o.glo), t);
+            }
+        }
+        for (int t = lane; t < P.nknot; t += nlanes) {
+            const OgbKnot K = P.knots[t];
+            if (K.var_prev == j) col.put(K.row, 1.0);
+            else if (K.var_post == j) col.put(K.row, -(K.u_post / K.u_prev));
+        }
+    } else {
+        const int sec = cd.blk;
+        for (int s = sec; s < P.nsec && s <= sec + 1; ++s) {
+            const OgbSec& S = ogb_sec(P, s);
+            double sign;
+            if (s == sec) sign = -0.5;
+            else if (S.t0_idx == j) sign = 0.5;
+            else continue;
+            for (int e = lane; e < S.ns * S.N; e += nlanes) {
+                const int b = e / S.N, i = e - b * S.N;
+                col.put(S.rdef + e, sign * W.sbase[b * P.gtot + S.g0 + i]);
+            }
+        }
+    }
+    if (cd.pick >= 0) {
+        for (int slot = lane; slot < P.sc_nouts; slot += nlanes) {
+            const ogb_out o = P.outs[P.sc_out_off + slot];
+            if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR)
+                col.put(o.row, W.scpert[slot * P.npick + cd.pick]);
+        }
+    }
+    if (lane == 0 && ogb_col_moves_cost(P, cd)) col.put(P.M - 1, W.costp[cl]);
 }

@@ -229,6 +229,7 @@ struct Session {
     double *p_d = nullptr, *lb_d = nullptr, *ub_d = nullptr, *c_d = nullptr, *vals_d = nullptr;
     double *DX_d = nullptr, *Jfull_d = nullptr;
     size_t work_bytes = 0;
+    int exact = 0;                  // 1: the session's Jacobians come from ogb_eval_exact (opt-in)
     std::vector<int64_t> soff;      // scatter offsets of the last ogb_host_eval_fd_scatter layout
     int soff_ld = -1, soff_mrows = -1;
     // pinned staging
@@ -315,6 +316,13 @@ void* ogb_host_session_create(void* prob, int max_batch, int chunk, int threads)
 
 void ogb_host_session_destroy(void* h) { delete (Session*)h; }
 
+int ogb_host_session_set_option(void* h, int key, int value) {
+    Session* S = (Session*)h;
+    if (!S) return fail("ogb_host_session_set_option: null session");
+    if (key == OGB_HOST_OPT_EXACT) { S->exact = value != 0; return 0; }
+    return fail("ogb_host_session_set_option: unknown key");
+}
+
 int ogb_host_session_stats(void* h, ogb_host_stats* out) {
     Session* S = (Session*)h;
     if (!S || !out) return fail("ogb_host_session_stats: null argument");
@@ -372,7 +380,9 @@ static int host_eval_core(Session* S, const double* p_h, const double* lb_h, con
         if (dma) {          // the plain dense transport: the dense J in HBM, one device -> host copy
             rc = ogb_eval_fd(S->prob, pk, S->lb_d, S->ub_d, abs_step, nb, ck, S->Jfull_d + (size_t)b0 * S->nM, S->DX_d, S->s_compute);
         } else {            // K1 + the sweep kernel with packed output: no dense J anywhere on the device
-            rc = ogb_eval_sparse(S->prob, pk, S->lb_d, S->ub_d, abs_step, nb, ck, S->vals_d + (size_t)b0 * S->nnz, S->DX_d, S->s_compute);
+            rc = S->exact
+                ? ogb_eval_exact(S->prob, pk, S->lb_d, S->ub_d, nb, ck, S->vals_d + (size_t)b0 * S->nnz, S->DX_d, S->s_compute)
+                : ogb_eval_sparse(S->prob, pk, S->lb_d, S->ub_d, abs_step, nb, ck, S->vals_d + (size_t)b0 * S->nnz, S->DX_d, S->s_compute);
         }
         if (rc) break;
         cudaEventRecord(S->ev_done[k], S->s_compute);

@@ -79,7 +79,12 @@ template <bool V> struct OgbBool { static constexpr bool value = V; };
 #ifndef OGB_MAX_THREADS
 #define OGB_MAX_THREADS 256
 #endif
-template <int NR>
+// PACKED_OUT = 0: c only / the dense J (zero stream + overwrites) / the probes; 1: the structurally
+// non-zero entries of the FD Jacobian into vals [B, nnz] (with_fd = 6); 2: the same entries of the EXACT
+// Jacobian (forward-mode tangents of the tapes + the analytic D-block, with_fd = 7).  Separate kernels rather
+// than run-time branches so that each gets its own register allocation (the dense column loop is
+// latency-bound and spill-free).
+template <int NR, int PACKED_OUT>
 __global__ void __launch_bounds__(OGB_MAX_THREADS, OGB_MIN_BLOCKS)
 ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const double* __restrict__ DX,
                  const double* __restrict__ lb, const double* __restrict__ ub, double abs_step,
@@ -253,7 +258,9 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         }
 
         // ---- phase 2: tapes -- base nodes, scalar program, one job per Jacobian column
-        if (with_fd != 5)        // (probe 5: no tapes, no assembly -- the zero stream alone)
+        if (PACKED_OUT == 2) {
+            for (int q = tid; q < P.gtot + 1 + ncols; q += nthr) ogb_job_exact(P, W, q, jlo);
+        } else if (with_fd != 5)        // (probe 5: no tapes, no assembly -- the zero stream alone)
         for (int q = tid; q < P.gtot + 1 + ncols; q += nthr) ogb_job(P, W, q, jlo, lb, ub, abs_step);
         if (tid == 0) *s_next = claimed;
         __syncthreads();
@@ -265,13 +272,17 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         if (with_fd != 5) ogb_assemble_base(P, W, tid, nthr);
         if (!P.has_running && with_fd != 5) {
             if (tid == 0) ogb_assemble_cost(P, W);
-            for (int cl = tid; cl < ncols; cl += nthr) ogb_cost_column(P, W, cl);
+            for (int cl = tid; cl < ncols; cl += nthr) {
+                if (PACKED_OUT == 2) ogb_cost_column_exact(P, W, cl); else ogb_cost_column(P, W, cl);
+            }
         }
         __syncthreads();
         if (P.has_running) {
             if (tid == 0) ogb_assemble_cost(P, W);
             __syncthreads();
-            for (int cl = tid; cl < ncols; cl += nthr) ogb_cost_column(P, W, cl);
+            for (int cl = tid; cl < ncols; cl += nthr) {
+                if (PACKED_OUT == 2) ogb_cost_column_exact(P, W, cl); else ogb_cost_column(P, W, cl);
+            }
             __syncthreads();
         }
         if (ch == 0)
@@ -440,8 +451,14 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 }
             }
         };
-        if (with_fd == 6) columns(OgbBool<true>{});
-        else columns(OgbBool<false>{});
+        if (PACKED_OUT == 2) {
+            // exact mode: one warp per column, every structural non-zero straight into the packed values
+            double* vb = J + (size_t)b * (size_t)P.nnz;
+            for (int cc = warp; cc < ncols; cc += nwarps)
+                ogb_scatter_column_exact(P, W, jlo + cc, cc, OgbColPacked{vb, P.pmap + (size_t)(jlo + cc) * (size_t)M}, lane, 32);
+        } else {
+            columns(OgbBool<PACKED_OUT != 0>{});
+        }
         __syncthreads();             // all warps are done reading this item's staging
         item = next_item;
     }

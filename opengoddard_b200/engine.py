@@ -179,6 +179,23 @@ class DeviceProblem:
                                                 work.data_ptr(), self._stream()), "ogb_eval_sparse")
         return c, vals
 
+    def eval_exact(self, P, out_c=None, out_vals=None):
+        """Exact mode (ogb_eval_exact): c (B, nrows) at clip(P) and the structural non-zeros of the exact
+        Jacobian -- analytic collocation block, forward-mode tangents of the traced tapes -- packed (B, nnz)
+        in the jac_pattern() layout; densify(vals) gives the dense matrix."""
+        t = self.torch
+        P = self._check_P(P)
+        B = P.shape[0]
+        c = out_c if out_c is not None else t.empty((B, self.nrows), dtype=t.float64, device=self.device)
+        vals = out_vals if out_vals is not None else t.empty((B, self.nnz), dtype=t.float64, device=self.device)
+        assert c.is_contiguous() and vals.is_contiguous()
+        work = self._workspace(B)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_eval_exact(self.h, P.data_ptr(), self.lb.data_ptr(), self.ub.data_ptr(), B,
+                                               c.data_ptr(), vals.data_ptr(), work.data_ptr(), self._stream()),
+                     "ogb_eval_exact")
+        return c, vals
+
     def densify(self, vals, out_J=None):
         """K2b alone: packed values (B, nnz) -> dense J (B, nvars, nrows), zeros included."""
         t = self.torch
@@ -195,11 +212,13 @@ class DeviceProblem:
             self._nnz = len(self.jac_pattern())
         return self._nnz
 
-    def host_evaluator(self):
-        """numpy-in / numpy-out evaluator for sqp.slsqp_batch (one per engine: it owns a host session)."""
-        if getattr(self, "_host_eval", None) is None:
-            self._host_eval = _HostEvaluator(self)
-        return self._host_eval
+    def host_evaluator(self, exact=False):
+        """numpy-in / numpy-out evaluator for sqp.slsqp_batch (one per engine and Jacobian flavour: it owns a
+        host session).  exact=True: the Jacobians are the exact ones (ogb_eval_exact) instead of FD."""
+        cache = self.__dict__.setdefault("_host_evals", {})
+        if bool(exact) not in cache:
+            cache[bool(exact)] = _HostEvaluator(self, exact=bool(exact))
+        return cache[bool(exact)]
 
     def autotune(self, P, candidates=(256, 384, 128), min_gain=0.02, reps=5):
         """Pick the CTA size of the NVRTC-specialised sweep kernel by timing ogb_sweep on the batch
@@ -242,9 +261,9 @@ class DeviceProblem:
         self.tuned_threads = choice
         return timings
 
-    def host_session(self, max_batch, chunk=0, threads=0):
+    def host_session(self, max_batch, chunk=0, threads=0, exact=False):
         """Host-buffer entry point (ogb_host_eval_fd): numpy / pinned host arrays in and out."""
-        return HostSession(self, max_batch, chunk, threads)
+        return HostSession(self, max_batch, chunk, threads, exact)
 
     def jac_pattern(self):
         """Ascending linear indices j * nrows + r of the entries of one instance's J that can be
@@ -308,9 +327,10 @@ class HostSession:
     C-contiguous.  mode: "dense" (J fully rewritten), "keep_zeros" (J already holds the problem's
     zero background), "packed" (J is (B, nnz)), "dma" (one dense device->host copy)."""
 
-    def __init__(self, eng, max_batch, chunk=0, threads=0):
+    def __init__(self, eng, max_batch, chunk=0, threads=0, exact=False):
         self.eng = eng
         self.max_batch = int(max_batch)
+        self.exact = bool(exact)
         self.lb = np.ascontiguousarray(eng.lb.cpu().numpy())
         self.ub = np.ascontiguousarray(eng.ub.cpu().numpy())
         with eng.torch.cuda.device(eng.device):
@@ -318,6 +338,8 @@ class HostSession:
         if not self.h:
             raise capi.OgbError("ogb_host_session_create failed: " + eng.b.error())
         self.nnz = len(eng.jac_pattern())
+        if self.exact:
+            eng._rc(eng.b.lib.ogb_host_session_set_option(self.h, 0, 1), "ogb_host_session_set_option")
 
     def close(self):
         if getattr(self, "h", None):
@@ -382,8 +404,9 @@ class HostSession:
 class _HostEvaluator:
     """numpy in / numpy out view of a DeviceProblem for sqp.slsqp_batch."""
 
-    def __init__(self, eng):
+    def __init__(self, eng, exact=False):
         self.eng = eng
+        self.exact = exact
         self.session = None
 
     def eval(self, X):
@@ -415,7 +438,7 @@ class _HostEvaluator:
         if self.session is None or self.session.max_batch < k:
             if self.session is not None:
                 self.session.close()
-            self.session = self.eng.host_session(max(k, 16))
+            self.session = self.eng.host_session(max(k, 16), exact=self.exact)
 
 
 def scipy_callables(eng, on_x=None, cost_derivative=None, args=()):

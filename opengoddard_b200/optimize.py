@@ -397,14 +397,24 @@ class Problem:
         """Batched hot path: P (B, nvars) -> c (B, m+1) [, J (B, nvars, m+1)] as torch CUDA
         tensors; row m carries cost / grad cost.  J[b, j, :] is column j.  host=True: P is a host
         array and the results come back as numpy arrays in host memory through the host-buffer
-        session (ogb_host_eval_fd: packed device->host transport, dense J rebuilt by host threads)."""
+        session (ogb_host_eval_fd: packed device->host transport, dense J rebuilt by host threads).
+        jacobian: True = SciPy's forward differences (the reference's Jacobian), "sparse" = the same as
+        packed values (B, nnz) in the engine's jac_pattern() layout, "exact" = the exact Jacobian (analytic
+        collocation block + forward-mode tangents of the callbacks; opt-in, packed), False = c only."""
         eng = self._engine_for(obj)
+        if jacobian in ("exact", "sparse"):
+            if host:
+                ev = eng.host_evaluator(exact=jacobian == "exact")
+                ev._session_for(len(P))
+                return ev.session.eval_fd(np.asarray(P, dtype=np.float64), mode="packed")
+            return eng.eval_exact(P) if jacobian == "exact" else eng.eval_sparse(P)
         if host:
             ev = eng.host_evaluator()
             return ev.eval_fd(np.asarray(P, dtype=np.float64)) if jacobian else ev.eval(np.asarray(P, dtype=np.float64))
         return eng.eval_fd(P) if jacobian else eng.eval(P)
 
-    def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None, processes=0):
+    def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None, processes=0,
+                    jacobian="fd"):
         """Multi-start: solve the NLP from every row of P0 (B, nvars) at once.
 
         Under an initialised torch.distributed process group (one rank per GPU) the rows of P0
@@ -418,16 +428,18 @@ class Problem:
         reach exit mode 0 are restarted from where they stopped, up to `max_outer`
         (default maxIterator) times.  `processes` > 1 steps the per-instance SLSQP cores in that many
         worker processes (SciPy's step holds the GIL, so this is what makes the host side scale with
-        the cores; sqp._ProcessStepper).  Returns dict(x, fun, status, nit, outer)."""
+        the cores; sqp._ProcessStepper).  jacobian="exact": SLSQP is given the exact Jacobians (opt-in; the
+        reference's are forward differences).  Returns dict(x, fun, status, nit, outer)."""
         from . import batch, sqp
         self._check_callbacks()
         eng = self._engine_for(obj)
         P0 = np.array(np.atleast_2d(P0), dtype=np.float64)
         return batch.run_sharded(
-            lambda rows: self._solve_rows(eng, rows, obj, ftol, maxiter, max_outer, threads, sqp, processes),
+            lambda rows: self._solve_rows(eng, rows, obj, ftol, maxiter, max_outer, threads, sqp, processes,
+                                          exact=(jacobian == "exact")),
             P0, group=group, device=eng.device)
 
-    def _solve_rows(self, eng, P0, obj, ftol, maxiter, max_outer, threads, sqp, processes=0):
+    def _solve_rows(self, eng, P0, obj, ftol, maxiter, max_outer, threads, sqp, processes=0, exact=False):
         lb, ub = self.bounds_arrays()
         X = np.array(np.atleast_2d(P0), dtype=np.float64).reshape(-1, self.number_of_variables)
         B = X.shape[0]
@@ -448,7 +460,7 @@ class Problem:
                 ids = np.nonzero(status != 0)[0]
                 if ids.size == 0:
                     break
-                res = sqp.slsqp_batch(eng.host_evaluator(), X[ids], lb, ub, eng.meq, eng.mineq, ftol=ftol,
+                res = sqp.slsqp_batch(eng.host_evaluator(exact=exact), X[ids], lb, ub, eng.meq, eng.mineq, ftol=ftol,
                                       maxiter=maxiter, cost_grad=grad, threads=threads,
                                       processes=pool if pool is not None else 0)
                 X[ids] = res["x"]

@@ -18,7 +18,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("OPENGODDARD_REF", "/root/reference")
+def _find_reference():
+    """$OPENGODDARD_REF, then /root/reference (the build container), then baseline/_ref (the
+    unmodified reference package pip-installed there with --target; it is git-ignored but travels
+    to the GPU box with the working tree, so bench.py's reference arm can time the real thing)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get("OPENGODDARD_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "OpenGoddard", "optimize.py")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 class _Chain:

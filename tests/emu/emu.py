@@ -19,6 +19,8 @@ def binding():
         dp = C.POINTER(C.c_double)
         b.lib.emu_eval.restype = C.c_int
         b.lib.emu_eval.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_int, dp, dp, C.c_int]
+        b.lib.emu_eval_exact.restype = C.c_int
+        b.lib.emu_eval_exact.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, dp]
         b.lib.emu_dx_gemm.restype = C.c_int
         b.lib.emu_dx_gemm.argtypes = [C.c_void_p, dp, C.c_int, dp]
         b.lib.emu_lgl_build.restype = C.c_int
@@ -46,6 +48,16 @@ class EmuProblem:
         J = np.empty((B, n, M))
         rc = self.b.lib.emu_eval(self.h, _ptr(P), _ptr(self.lb), _ptr(self.ub), abs_step, B,
                                  _ptr(c), _ptr(J), 1)
+        assert rc == 0
+        return c, J
+
+    def eval_exact(self, P):
+        """c at clip(P) and the exact (forward-mode / analytic) Jacobian, dense (B, n, M)."""
+        P = np.ascontiguousarray(np.atleast_2d(P), dtype=np.float64)
+        B, n, M = P.shape[0], self.info.nvars, self.info.nrows
+        c = np.empty((B, M))
+        J = np.empty((B, n, M))
+        rc = self.b.lib.emu_eval_exact(self.h, _ptr(P), _ptr(self.lb), _ptr(self.ub), B, _ptr(c), _ptr(J))
         assert rc == 0
         return c, J
 

@@ -102,4 +102,43 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
     return 0;
 }
 
+// exact mode: c at clip(p) and the analytic / forward-mode Jacobian, dense J [B, n, M]
+int emu_eval_exact(void* h, const double* p, const double* lb, const double* ub, int B, double* c, double* J) {
+    OgbHostProblem* H = (OgbHostProblem*)h;
+    const OgbProb& P = H->P;
+    OgbPlan pl = H->plan;
+    std::vector<double> mem(pl.o_end, 0.0);
+    OgbWork W;
+    W.sp = mem.data() + pl.o_sp; W.sdx = mem.data() + pl.o_sdx; W.sbase = mem.data() + pl.o_sbase;
+    W.sc = mem.data() + pl.o_sc; W.scbase = mem.data() + pl.o_scbase; W.coef = mem.data() + pl.o_coef;
+    W.prefix = mem.data() + pl.o_prefix; W.pert = mem.data() + pl.o_pert; W.pdx = mem.data() + pl.o_pdx;
+    W.px1 = mem.data() + pl.o_px1; W.scpert = mem.data() + pl.o_scpert; W.G = pl.G;
+    W.pdlt = mem.data() + pl.o_pdlt; W.pcol = reinterpret_cast<OgbCol*>(mem.data() + pl.o_pcol);
+    W.cf = mem.data() + pl.o_cf; W.rterm = mem.data() + pl.o_rterm; W.costp = mem.data() + pl.o_costp; W.prdx = mem.data() + pl.o_prdx;
+    std::vector<double> tilev(P.M), pclip(P.n), dxs(P.ndx);
+    double* tile = tilev.data();
+    for (int b = 0; b < B; ++b) {
+        for (int j = 0; j < P.n; ++j) pclip[j] = fmin(fmax(p[(size_t)b * P.n + j], lb[j]), ub[j]);
+        emu_dx_gemm(h, pclip.data(), 1, dxs.data());
+        for (int ch = 0; ch < pl.split; ++ch) {
+            const int jlo = ch * pl.group;
+            const int ncols = std::min(pl.group, P.n - jlo);
+            for (int j = 0; j < P.n; ++j) W.sp[j] = pclip[j];
+            for (int e = 0; e < P.ndx; ++e) W.sdx[e] = dxs[e];
+            for (int q = 0; q < P.gtot + 1 + ncols; ++q) ogb_job_exact(P, W, q, jlo);
+            ogb_assemble_base(P, W, 0, 1);
+            ogb_assemble_cost(P, W);
+            for (int cl = 0; cl < ncols; ++cl) ogb_cost_column_exact(P, W, cl);
+            if (ch == 0) memcpy(c + (size_t)b * P.M, W.sc, sizeof(double) * P.M);
+            for (int cl = 0; cl < ncols; ++cl) {
+                for (int r = 0; r < P.M; ++r) tile[r] = 0.0;
+                OgbColOut out{tile, tile + P.meq, P.meq};
+                ogb_scatter_column_exact(P, W, jlo + cl, cl, out, 0, 1);
+                memcpy(J + ((size_t)b * P.n + jlo + cl) * P.M, tile, sizeof(double) * P.M);
+            }
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"
