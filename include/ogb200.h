@@ -115,6 +115,9 @@ typedef struct ogb_problem_desc {
     const ogb_table* tables_h;        /* [ntables]                                    */
     const double* table_x_h;          /* concatenated abscissae                       */
     const double* table_y_h;          /* concatenated ordinates                       */
+    const double* unit_controls_h;    /* unit_controls, phases concatenated [sum ncontrols]; NULL = all 1.
+                                         Only the guess / trajectory kernels use it (inside the traced
+                                         callbacks the units are already part of the tapes)            */
 } ogb_problem_desc;
 
 typedef struct ogb_problem_info {
@@ -231,6 +234,41 @@ int ogb_eval_fd(void* prob, const double* p, const double* lb, const double* ub,
 int ogb_eval_sparse(void* prob, const double* p, const double* lb, const double* ub, double abs_step,
                     int B, double* c, double* vals, void* work, void* stream);
 int ogb_densify(void* prob, const double* vals, int B, double* J, void* stream);
+
+/* ---- initial guesses and post-processing on the device ------------------
+ * Batched counterparts of the reference's one-instance host helpers, so that large multi-start batches
+ * are generated, perturbed and unpacked without a host round trip.
+ *
+ * ogb_guess_fill: Guess.zeros / constant / linear / cubic (reference optimize.py:883-956) evaluated on the
+ * problem's LGL time nodes and stored the way set_states / set_controls(_all_section) store them (value /
+ * unit, :377-440).  Spec i writes block `blk` (states first, then controls) of phase `sec`, or of every
+ * phase over the concatenated time axis when sec = -1 (the *_all_section calls the shipped examples make:
+ * examples/04_Goddard_0knot.py:115-140); instance b takes its parameters from params[b, i, 0..3]:
+ * constant c | linear (y0, yf) | cubic (y0, y'0, yf, y'f).  time_nodes [total_nodes]: prob.time_all_section.
+ * tfinal (may be NULL) [B, nsec]: final times to store (set_time_final, :437-440).  Entries of P no spec
+ * covers are left untouched.                                                                          */
+enum ogb_guess_kind { OGB_GUESS_ZEROS = 0, OGB_GUESS_CONSTANT = 1, OGB_GUESS_LINEAR = 2, OGB_GUESS_CUBIC = 3 };
+typedef struct ogb_guess_spec {
+    int32_t sec, blk, kind, pad;
+} ogb_guess_spec;
+int ogb_guess_fill(void* prob, const ogb_guess_spec* specs_h, int nspec, const double* params /*[B, nspec, 4]*/,
+                   const double* time_nodes /*[total_nodes]*/, const double* tfinal /*[B, nsec] or NULL*/, int B,
+                   double* P /*[B, nvars]*/, void* stream);
+
+/* ogb_jitter: the multi-start perturbation of a batch of decision vectors, in place:
+ *   state / control entries  p <- p * (1 + rel_x * z),  z ~ N(0, 1);   final times  p <- p * (1 + rel_t * u),
+ *   u ~ U[-1, 1);   then clipped into [lb, ub] (either may be NULL).
+ * Counter-based generator (Philox4x32-10, key = seed, counter = (variable, 0, first_instance + b, 0); Box-Muller
+ * on two 53-bit uniforms), so any sub-range of instances is reproducible on any number of GPUs; restated
+ * in numpy by oracle/og_rng.py for the parity test.                                                    */
+int ogb_jitter(void* prob, double* P, int B, uint64_t seed, int64_t first_instance, double rel_x, double rel_t,
+               const double* lb, const double* ub, void* stream);
+
+/* ogb_trajectories: what Problem.time_update / states_all_section / controls_all_section / to_csv assemble
+ * per instance (reference optimize.py:518-531, :286-331, :844-863): out [B, total_nodes, 1 + ns + nc] holds per
+ * node the dimensional time ((t_{s+1} - t_s) / 2 * tau + (t_{s+1} + t_s) / 2 with t = [0, final times], as the
+ * reference assumes t0 = 0 there), states and controls (p * unit); ns / nc are those of phase 0, as in to_csv. */
+int ogb_trajectories(void* prob, const double* P, int B, double* out, void* stream);
 
 /* ---- exact Jacobian mode (opt-in) ------------------------------------
  * The same rows and columns with derivatives instead of difference quotients: the collocation block is

@@ -30,6 +30,13 @@ class OgbTable(C.Structure):
                 ("fill_below", C.c_double), ("fill_above", C.c_double)]
 
 
+class OgbGuessSpec(C.Structure):
+    _fields_ = [("sec", C.c_int32), ("blk", C.c_int32), ("kind", C.c_int32), ("pad", C.c_int32)]
+
+
+GUESS_KINDS = {"zeros": 0, "constant": 1, "linear": 2, "cubic": 3}       # enum ogb_guess_kind
+
+
 class OgbProblemDesc(C.Structure):
     _fields_ = [("nsec", C.c_int32),
                 ("nodes_h", C.POINTER(C.c_int32)),
@@ -47,7 +54,8 @@ class OgbProblemDesc(C.Structure):
                 ("ntables", C.c_int32),
                 ("tables_h", C.POINTER(OgbTable)),
                 ("table_x_h", C.POINTER(C.c_double)),
-                ("table_y_h", C.POINTER(C.c_double))]
+                ("table_y_h", C.POINTER(C.c_double)),
+                ("unit_controls_h", C.POINTER(C.c_double))]
 
 
 class OgbProblemInfo(C.Structure):
@@ -108,7 +116,8 @@ def make_desc(ir):
         float(ir.unit_time), float(ir.t0),
         arr([1 if k else 0 for k in ir.knot_smooth], C.c_uint8, np.uint8),
         int(ir.meq_user), int(ir.mineq_user), 1 if ir.has_running_cost else 0, progs, scalar,
-        len(ir.tables), tabs, arr(tx, C.c_double, np.float64), arr(ty, C.c_double, np.float64))
+        len(ir.tables), tabs, arr(tx, C.c_double, np.float64), arr(ty, C.c_double, np.float64),
+        arr(getattr(ir, "unit_controls", None) or [1.0] * max(1, sum(ir.ncontrols)), C.c_double, np.float64))
     return desc, keep
 
 
@@ -188,6 +197,12 @@ def ogb():
         L.ogb_densify.argtypes = [vp, dp, i32, dp, vp]
         L.ogb_host_eval_fd_scatter.restype = C.c_int
         L.ogb_host_eval_fd_scatter.argtypes = [vp, vp, vp, vp, C.c_double, i32, vp, vp, i32, i32, vp]
+        L.ogb_guess_fill.restype = C.c_int
+        L.ogb_guess_fill.argtypes = [vp, C.POINTER(OgbGuessSpec), i32, dp, dp, dp, i32, dp, vp]
+        L.ogb_jitter.restype = C.c_int
+        L.ogb_jitter.argtypes = [vp, dp, i32, C.c_uint64, C.c_int64, C.c_double, C.c_double, dp, dp, vp]
+        L.ogb_trajectories.restype = C.c_int
+        L.ogb_trajectories.argtypes = [vp, dp, i32, dp, vp]
         L.ogb_jac_pattern.restype = C.c_int
         L.ogb_jac_pattern.argtypes = [vp, vp, i32]
         L.ogb_pack.restype = C.c_int

@@ -73,7 +73,9 @@ struct OgbProb {
     const double* D;        // row-major per phase
     const double* Dt;       // transposed per phase
     const double* w;        // LGL weights, phases concatenated
+    const double* tau;      // LGL nodes, phases concatenated
     const double* ustate;
+    const double* ucontrol; // unit_controls, phases concatenated (guess / trajectory kernels only)
     const OgbKnot* knots;
     const OgbCol* cols;
     const int* pickvars;

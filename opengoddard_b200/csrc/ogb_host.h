@@ -21,7 +21,7 @@ struct OgbHostProblem {
     std::vector<OgbSec> sec;
     std::vector<ogb_out> outs;
     std::vector<uint64_t> code;
-    std::vector<double> consts, D, Dt, w, tau, ustate;
+    std::vector<double> consts, D, Dt, w, tau, ustate, ucontrol;
     std::vector<OgbKnot> knots;
     std::vector<OgbCol> cols;
     std::vector<int> pickvars;
@@ -35,6 +35,7 @@ struct OgbHostProblem {
     void bind_host() {
         P.sec = sec.data(); P.outs = outs.data(); P.code = code.data(); P.consts = consts.data();
         P.D = D.data(); P.Dt = Dt.data(); P.w = w.data(); P.ustate = ustate.data();
+        P.tau = tau.data(); P.ucontrol = ucontrol.data();
         P.knots = knots.data(); P.cols = cols.data(); P.pickvars = pickvars.data();
         P.tables = tables.data(); P.tab_x = tab_x.data(); P.tab_y = tab_y.data();
     }
@@ -163,6 +164,13 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
     P.ndx = dxoff;
     if (P.n > OGB_MAX_FIELD) { delete H; return fail("too many variables for the 14-bit tape operand field"); }
     H->ustate.assign(d->unit_states_h, d->unit_states_h + usoff);
+    {
+        int ncs = 0;
+        for (const OgbSec& S : H->sec) ncs += S.nc;
+        if (d->unit_controls_h) H->ucontrol.assign(d->unit_controls_h, d->unit_controls_h + ncs);
+        else H->ucontrol.assign((size_t)std::max(1, ncs), 1.0);
+        if (H->ucontrol.empty()) H->ucontrol.push_back(1.0);
+    }
     H->D.resize(doff); H->Dt.resize(doff); H->w.resize(g0); H->tau.resize(g0);
     for (int s = 0; s < d->nsec; ++s) {
         OgbSec& S = H->sec[s];

@@ -196,6 +196,66 @@ class DeviceProblem:
                      "ogb_eval_exact")
         return c, vals
 
+    # ------------------------------------------------------------------ guesses / starts / trajectories
+    def guess_batch(self, specs, params, time_nodes, tfinal=None, out=None, base=None):
+        """ogb_guess_fill: a batch of initial guesses built on the device.  specs: list of
+        (kind, block, section) with kind in "zeros" / "constant" / "linear" / "cubic", block = state number or
+        nstates + control number, section = phase or None for every phase over the concatenated time axis
+        (the reference's Guess.*(prob.time_all_section, ...) + set_*_all_section); params (B, len(specs), 4);
+        time_nodes = prob.time_all_section; tfinal (B, nsec) optional.  Entries no spec covers come from
+        `base` (n,) (default zeros).  Returns P (B, nvars) on the device."""
+        t = self.torch
+        params = t.as_tensor(np.ascontiguousarray(params, dtype=np.float64), device=self.device) \
+            if not isinstance(params, t.Tensor) else params.to(self.device, t.float64).contiguous()
+        B, ns = int(params.shape[0]), len(specs)
+        assert tuple(params.shape) == (B, ns, 4)
+        tn = t.as_tensor(np.ascontiguousarray(time_nodes, dtype=np.float64), device=self.device)
+        assert tn.numel() == self.info.total_nodes
+        tf = None
+        if tfinal is not None:
+            tf = t.as_tensor(np.ascontiguousarray(tfinal, dtype=np.float64), device=self.device) \
+                if not isinstance(tfinal, t.Tensor) else tfinal.to(self.device, t.float64).contiguous()
+            assert tf.shape[0] == B and tf.numel() == B * len(self.ir.nodes)
+        P = out if out is not None else t.zeros((B, self.nvars), dtype=t.float64, device=self.device)
+        if base is not None:
+            P[:] = t.as_tensor(np.asarray(base, dtype=np.float64), device=self.device)
+        arr = (capi.OgbGuessSpec * max(1, ns))()
+        for i, (kind, blk, sec) in enumerate(specs):
+            arr[i] = capi.OgbGuessSpec(-1 if sec is None else int(sec), int(blk), capi.GUESS_KINDS[kind], 0)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_guess_fill(self.h, arr, ns, params.data_ptr(), tn.data_ptr(),
+                                               tf.data_ptr() if tf is not None else None, B, P.data_ptr(),
+                                               self._stream()), "ogb_guess_fill")
+        return P
+
+    def jitter_(self, P, seed, first=0, rel_x=0.01, rel_t=0.05, clip=True):
+        """ogb_jitter, in place: the seeded multi-start perturbation of a device batch P (B, nvars)."""
+        t = self.torch
+        assert isinstance(P, t.Tensor) and P.is_contiguous() and P.dtype == t.float64 and P.device == self.device
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_jitter(self.h, P.data_ptr(), int(P.shape[0]), int(seed), int(first), float(rel_x),
+                                           float(rel_t), self.lb.data_ptr() if clip else None,
+                                           self.ub.data_ptr() if clip else None, self._stream()), "ogb_jitter")
+        return P
+
+    def make_starts(self, p0, B, seed, first=0, rel_x=0.01, rel_t=0.05):
+        """B perturbed copies of the guess p0 (n,), generated on the device (nothing crosses PCIe but p0)."""
+        t = self.torch
+        P = t.as_tensor(np.asarray(p0, dtype=np.float64), device=self.device).repeat(int(B), 1).contiguous()
+        return self.jitter_(P, seed, first, rel_x, rel_t)
+
+    def trajectories(self, P):
+        """ogb_trajectories: (B, total_nodes, 1 + ns + nc) -- time, states, controls per node, dimensional
+        (what time_update / states_all_section / controls_all_section / to_csv give per instance)."""
+        t = self.torch
+        P = self._check_P(P)
+        W = 1 + self.ir.nstates[0] + self.ir.ncontrols[0]
+        out = t.empty((P.shape[0], self.info.total_nodes, W), dtype=t.float64, device=self.device)
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_trajectories(self.h, P.data_ptr(), int(P.shape[0]), out.data_ptr(), self._stream()),
+                     "ogb_trajectories")
+        return out
+
     def densify(self, vals, out_J=None):
         """K2b alone: packed values (B, nnz) -> dense J (B, nvars, nrows), zeros included."""
         t = self.torch

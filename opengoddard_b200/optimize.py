@@ -413,6 +413,31 @@ class Problem:
             return ev.eval_fd(np.asarray(P, dtype=np.float64)) if jacobian else ev.eval(np.asarray(P, dtype=np.float64))
         return eng.eval_fd(P) if jacobian else eng.eval(P)
 
+    def make_starts(self, B, obj=None, seed=20261017, first=0, rel_states=0.01, rel_time=0.05):
+        """B multi-start decision vectors around the current guess `self.p`, generated ON THE DEVICE
+        (engine.make_starts: counter-based Philox jitter, 1 % Gaussian on states / controls, +-5 % uniform on
+        the final times, clipped into the bounds).  Returns a (B, nvars) CUDA tensor; instance `first + i` is
+        the same whatever B or the number of GPUs."""
+        eng = self._engine_for(obj)
+        return eng.make_starts(self.p, B, seed, first, rel_states, rel_time)
+
+    def guess_batch(self, specs, params, obj=None, tfinal=None):
+        """A batch of guesses from per-instance boundary values, on the device (engine.guess_batch):
+        specs = [("linear", ("state", 0), None), ("cubic", ("control", 0), 1), ...] name the generator, the
+        variable and the phase (None = all phases, like Guess.*(prob.time_all_section) + set_*_all_section);
+        params (B, len(specs), 4) hold const | (y0, yf) | (y0, y'0, yf, y'f) per instance."""
+        eng = self._engine_for(obj)
+        low = []
+        for kind, (what, k), sec in specs:
+            ns = self.number_of_states[0 if sec is None else sec]
+            low.append((kind, k if what == "state" else ns + k, sec))
+        return eng.guess_batch(low, params, self.time_all_section, tfinal=tfinal, base=self.p)
+
+    def trajectories(self, P, obj=None):
+        """time / states / controls of every instance of P at every node, dimensional, on the device:
+        (B, total nodes, 1 + nstates + ncontrols) -- the batched time_update + *_all_section + to_csv table."""
+        return self._engine_for(obj).trajectories(P)
+
     def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None, processes=0,
                     jacobian="fd"):
         """Multi-start: solve the NLP from every row of P0 (B, nvars) at once.

@@ -127,6 +127,7 @@ class ProblemIR:
     nvars: int = 0
     tables: list = field(default_factory=list)   # dicts: x, y, variant, extrapolate, fill_below, fill_above
     meta: dict = field(default_factory=dict)
+    unit_controls: list = field(default_factory=list)   # flattened over phases (guess / trajectory kernels only)
 
 
 class _RowBuilder:
@@ -279,7 +280,8 @@ def _build_ir(prob, obj):
         meq_user=eq.nrows, mineq_user=ineq.nrows, has_running_cost=run_parts is not None,
         node_tapes=node_tapes, scalar_tape=scalar_tape, nvars=ctx.nvars,
         tables=[{k: v for k, v in t.items() if k != "keep"} for t in ctx.tables],
-        meta={"graph_nodes": len(g.nodes)})
+        meta={"graph_nodes": len(g.nodes)},
+        unit_controls=[float(u) for s in range(nsec) for u in prob.unit_controls[s][:ctx.ncontrols[s]]])
 
 
 # ------------------------------------------------------------------ (de)serialisation
@@ -292,7 +294,8 @@ def ir_to_arrays(ir):
            "scalars": np.array([ir.unit_time, ir.t0], dtype=np.float64),
            "flags": np.array([ir.meq_user, ir.mineq_user, int(ir.has_running_cost), ir.nvars, len(ir.tables)],
                              dtype=np.int64),
-           "knot_smooth": np.array([1 if k else 0 for k in ir.knot_smooth], dtype=np.uint8)}
+           "knot_smooth": np.array([1 if k else 0 for k in ir.knot_smooth], dtype=np.uint8),
+           "unit_controls": np.array(ir.unit_controls, dtype=np.float64)}
     for name, tp in [("node%d" % s, t) for s, t in enumerate(ir.node_tapes)] + [("scalar", ir.scalar_tape)]:
         out[name + "_code"] = np.asarray(tp.code, dtype=np.uint64)
         out[name + "_consts"] = np.asarray(tp.consts, dtype=np.float64)
@@ -325,4 +328,5 @@ def ir_from_arrays(d):
                      unit_time=float(d["scalars"][0]), t0=float(d["scalars"][1]),
                      knot_smooth=[bool(v) for v in d["knot_smooth"]], meq_user=flags[0], mineq_user=flags[1],
                      has_running_cost=bool(flags[2]), node_tapes=[tp("node%d" % s) for s in range(nsec)],
-                     scalar_tape=tp("scalar"), nvars=flags[3], tables=tables, meta={"loaded": True})
+                     scalar_tape=tp("scalar"), nvars=flags[3], tables=tables, meta={"loaded": True},
+                     unit_controls=[float(v) for v in d["unit_controls"]] if "unit_controls" in d else [])

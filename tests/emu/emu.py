@@ -21,6 +21,12 @@ def binding():
         b.lib.emu_eval.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_int, dp, dp, C.c_int]
         b.lib.emu_eval_exact.restype = C.c_int
         b.lib.emu_eval_exact.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, dp]
+        b.lib.emu_guess_value.restype = C.c_double
+        b.lib.emu_guess_value.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, dp]
+        b.lib.emu_philox4x32.restype = None
+        b.lib.emu_philox4x32.argtypes = [C.POINTER(C.c_uint32)] * 3
+        b.lib.emu_u53.restype = C.c_double
+        b.lib.emu_u53.argtypes = [C.c_uint32, C.c_uint32]
         b.lib.emu_dx_gemm.restype = C.c_int
         b.lib.emu_dx_gemm.argtypes = [C.c_void_p, dp, C.c_int, dp]
         b.lib.emu_lgl_build.restype = C.c_int

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../opengoddard_b200/csrc/ogb_host.h"
+#include "../../opengoddard_b200/csrc/ogb_guess.cuh"
 
 static std::string g_err;
 
@@ -101,6 +102,16 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
     }
     return 0;
 }
+
+double emu_guess_value(int kind, double t, double t0, double tf, const double* q) {
+    return ogb_guess_value(kind, t, t0, tf, q);
+}
+
+void emu_philox4x32(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    ogb_philox4x32(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+
+double emu_u53(uint32_t a, uint32_t b) { return ogb_u53(a, b); }
 
 // exact mode: c at clip(p) and the analytic / forward-mode Jacobian, dense J [B, n, M]
 int emu_eval_exact(void* h, const double* p, const double* lb, const double* ub, int B, double* c, double* J) {
