@@ -18,8 +18,12 @@ Timing: W >= 3 warm-up steps, then exactly K timed steps, each bracketed by CUDA
 on the launching stream; a 256 MiB memset flushes L2 between steps outside the event
 pairs (each step also writes ~3 GB, 24x L2).  Time = sum of the K event durations, MAX
 over ranks.  `e2e` repeats the measurement through the host-buffer C-ABI call
-(ogb_host_eval_fd): pinned host p -> H2D -> K1 -> K2 -> K3 pack -> D2H of c and the packed non-zeros
--> host threads write the dense J into host memory, all inside the timed region (host clock).
+(ogb_host_eval_fd): pinned host p -> H2D -> K1 -> K2a (sweep kernel, packed output) -> D2H of c and the
+packed non-zeros -> host threads write the dense J into host memory, all inside the timed region (host
+clock).  Also in the line (set-up or after the timed region, never inside it): `parity` (3 instances
+against the numpy oracle), `tensor` (K1 against a measured FP64 DGEMM peak), `e2e_sqp` (the transport the
+SQP driver uses: packed values scattered into per-instance SLSQP buffers), `extra` (single-instance
+latency, the sparse / exact evaluation rates, a batched multi-start solve next to the CPU reference).
 """
 import argparse
 import json
@@ -269,6 +273,218 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+# ------------------------------------------------------------------ checks and extras of the CUDA arm
+def parity_check(eng, cfg, workloads, P3):
+    """c and J of the first instances against the numpy oracle, outside the timed region (the tolerances are
+    the tests': |dc| <= 1e-6 max(|c|, 1e-6 terms), |dJ| <= 1e-6 rowmax, zero pattern up to FD dust)."""
+    import numpy as np
+    from oracle import og_numpy
+    wo = workloads.build(cfg, og_numpy)
+    lb, ub = og_numpy.bounds_arrays(wo.prob)
+    c, J = eng.eval_fd(P3)
+    c, J = c.cpu().numpy(), J.cpu().numpy()
+    out = {"instances": int(len(P3)), "c_max_rel": 0.0, "J_rowscaled_max": 0.0, "zero_mismatch": 0, "ok": True}
+    for b in range(len(P3)):
+        c_ref, J_ref = og_numpy.eval_fd(wo.prob, wo.obj, P3[b], lb, ub)
+        x = np.clip(P3[b], lb, ub)
+        terms = (np.abs(J_ref) * np.abs(x)[None, :]).sum(axis=1)
+        scale = np.maximum(np.abs(c_ref), 1e-6 * terms)
+        out["c_max_rel"] = max(out["c_max_rel"], float((np.abs(c[b] - c_ref) / np.maximum(scale, 1e-300)).max()))
+        rowmax = np.abs(J_ref).max(axis=1, keepdims=True)
+        Jb = J[b].T
+        out["J_rowscaled_max"] = max(out["J_rowscaled_max"], float((np.abs(Jb - J_ref) / np.maximum(rowmax, 1e-300)).max()))
+        mism = (Jb == 0) != (J_ref == 0)
+        big = np.maximum(np.abs(Jb), np.abs(J_ref)) > 1e-7 * rowmax
+        out["zero_mismatch"] += int((mism & big).sum())
+        out["zero_mismatch_dust"] = out.get("zero_mismatch_dust", 0) + int((mism & ~big).sum())
+    out["ok"] = bool(out["c_max_rel"] <= 1e-6 and out["J_rowscaled_max"] <= 1e-6 and out["zero_mismatch"] == 0)
+    out["against"] = "oracle/og_numpy.py (bit-identical to the reference-generated goldens, tests/test_oracle.py)"
+    assert out["ok"], "bench.py parity check failed: %r" % (out,)
+    return out
+
+
+def tensor_check(eng, wl, P, torch):
+    """K1 (the batched FP64 tensor-core GEMM D.X) timed alone against the FP64 DGEMM peak measured here with
+    cuBLAS (torch.matmul f64 4096^3, best of 5) -- MEASURED_PEAKS.json has no FP64 entry."""
+    dev = P.device
+    N = 4096
+    a = torch.randn((N, N), dtype=torch.float64, device=dev)
+    b = torch.randn((N, N), dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.matmul(a, b)
+    best = float("inf")
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    peak = 2.0 * N ** 3 / (best * 1e-3) / 1e12
+    del a, b
+    DX = eng.dx_gemm(P, clip=True)
+    for _ in range(3):
+        eng.dx_gemm(P, out=DX, clip=True)
+    k1 = float("inf")
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.dx_gemm(P, out=DX, clip=True)
+        e1.record()
+        e1.synchronize()
+        k1 = min(k1, e0.elapsed_time(e1))
+    prob = wl.prob
+    flop = 2.0 * sum(N_ * N_ * ns for N_, ns in zip(prob.nodes, prob.number_of_states)) * P.shape[0]
+    pipe = None
+    try:
+        pipe = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k1_tensor_pipe_pct")
+    except (OSError, ValueError):
+        pass
+    return {"kernel": "ogb_dx_gemm_kernel (K1, mma.sync m8n8k4 f64 = DMMA; tcgen05 has no f64 kind)",
+            "flop_per_launch": flop, "k1_ms_alone": k1, "k1_tflops": flop / (k1 * 1e-3) / 1e12,
+            "dgemm_peak_tflops": peak, "dgemm_peak_how": "torch.matmul float64 4096^3 (cuBLAS), best of 5, CUDA events",
+            "frac": flop / (k1 * 1e-3) / 1e12 / peak, "pipe_pct_from_ncu": pipe,
+            "note": "K1 is 2 N^2 nstates FLOP per instance (15 kFLOP at Goddard-50): memory / latency bound by "
+                    "construction, ~5 % of a step"}
+
+
+def extras(eng, wl, cfg, workloads, P, P_host, torch, args, api):
+    import numpy as np
+    dev = P.device
+    B = P.shape[0]
+    n, M = eng.nvars, eng.nrows
+    out = {}
+
+    def best_ms(fn, reps=5):
+        for _ in range(2):
+            fn()
+        best = float("inf")
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+    # ---- sparse FD and exact Jacobians (packed output), device-resident
+    try:
+        nnz = eng.nnz
+        c = torch.empty((B, M), dtype=torch.float64, device=dev)
+        vals = torch.empty((B, nnz), dtype=torch.float64, device=dev)
+        sparse_bytes = 8 * n + 8 * M + 8 * nnz
+        peak = 6437.9
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak))
+        except (OSError, ValueError):
+            pass
+        for name, fn in (("sparse_fd", lambda: eng.eval_sparse(P, out_c=c, out_vals=vals)),
+                         ("exact", lambda: eng.eval_exact(P, out_c=c, out_vals=vals))):
+            ms = best_ms(fn)
+            out[name] = {"evals_per_s": B / (ms * 1e-3), "ms_per_step": ms, "nnz": int(nnz),
+                         "algorithmic_bytes_per_eval": sparse_bytes,
+                         "roofline": {"bound": "hbm", "achieved": B * sparse_bytes / (ms * 1e-3) / 1e9, "peak": peak,
+                                      "unit": "GB/s", "frac": B * sparse_bytes / (ms * 1e-3) / 1e9 / peak,
+                                      "note": "K1 + the sweep kernel with packed output; latency / issue bound, "
+                                              "not HBM bound (8 n + 8 M + 8 nnz bytes per eval)"}}
+        # how far the two Jacobians are apart (FD truncation + rounding noise, row-scaled)
+        _, v_fd = eng.eval_sparse(P[:64])
+        _, v_ex = eng.eval_exact(P[:64])
+        Jf, Je = eng.densify(v_fd), eng.densify(v_ex)
+        rowmax = Je.abs().amax(dim=1, keepdim=True).clamp_min(1e-300)
+        out["exact"]["fd_vs_exact_rowscaled_max"] = float(((Jf - Je).abs() / rowmax).max())
+        del Jf, Je, c, vals
+    except Exception as ex:
+        out["sparse_error"] = str(ex)[:200]
+    # ---- a single instance per call (what Problem.solve does at every SLSQP iteration): latency
+    try:
+        import time as _t
+        eng1 = wl.prob.compile(wl.obj, device=dev, jit=False)
+        x = P_host[0].numpy().copy()
+        for _ in range(5):
+            eng1.eval_fd_host(x)
+        t0 = _t.perf_counter()
+        for _ in range(50):
+            eng1.eval_fd_host(x)
+        fd_us = (_t.perf_counter() - t0) / 50 * 1e6
+        t0 = _t.perf_counter()
+        for _ in range(50):
+            eng1.eval_host(x)
+        out["latency_b1"] = {"eval_fd_host_us": fd_us, "eval_host_us": (_t.perf_counter() - t0) / 50 * 1e6,
+                             "what": "one instance, host vector in, c and the dense J back in host memory "
+                                     "(pinned staging, interpreter kernel as Problem.solve uses it)"}
+    except Exception as ex:
+        out["latency_error"] = str(ex)[:200]
+    # ---- the product's real end to end: a batched multi-start solve (SLSQP cores in worker processes fed by
+    #      the scatter transport), next to the reference's way of doing the same iterations on this host
+    try:
+        import time as _t
+        S = max(1, int(args.solve_starts))
+        iters = 4
+        procs = host_procs()
+        X0 = P_host[:S].numpy().copy()
+        wl.prob._engine, wl.prob._engine_key = eng, wl.prob._fingerprint(wl.obj, True)
+        t0 = _t.perf_counter()
+        res = wl.prob.solve_batch(X0, wl.obj, ftol=1e-10, maxiter=iters, max_outer=1, processes=procs)
+        wall = _t.perf_counter() - t0
+        done = int(np.asarray(res["nit"]).sum())
+        ev = eng.host_evaluator()
+        t0 = _t.perf_counter()
+        reps = 3
+        Cs = np.zeros((S, n, M - 1))
+        Gs = np.zeros((S, n))
+        for _ in range(reps):
+            ev.eval_fd_scatter(X0, [Cs.ctypes.data + b * Cs.strides[0] for b in range(S)], M - 1, M - 1,
+                               [Gs.ctypes.data + b * Gs.strides[0] for b in range(S)])
+        dev_s = (_t.perf_counter() - t0) / reps
+        out["solve_batch"] = {"starts": S, "slsqp_iterations_each": iters, "processes": procs,
+                              "instance_iterations_per_s": done / wall, "wall_s": wall, "instance_iterations": done,
+                              "device_eval_s_per_iteration": dev_s,
+                              "device_share": min(1.0, dev_s * (iters + 1) / wall),
+                              "what": "Problem.solve_batch: lock-step SLSQP (SciPy's C core, one state per instance "
+                                      "in worker processes) over one batched device evaluation per round; includes "
+                                      "starting the worker processes"}
+        out["solve_batch"]["reference"] = reference_solve_rate(cfg, iters)
+    except Exception as ex:
+        out["solve_error"] = str(ex)[:300]
+    return out
+
+
+def reference_solve_rate(cfg, iters):
+    """SLSQP iterations per second the CPU path achieves on one core for the same problem: scipy.minimize on
+    the reference's (or the port's) closures, FD Jacobians by SciPy -- what Problem.solve of the reference does."""
+    import contextlib
+    import io
+    import numpy as np
+    from scipy import optimize
+    from opengoddard_b200 import workloads
+    kind = cpu_kind()
+    if kind == "reference":
+        from oracle import ref_loader
+        mod = ref_loader.load_reference()
+        wl = workloads.build(cfg, mod)
+        cap = ref_loader.capture_solve(mod, wl.prob, wl.obj)
+        fun, args_, cons, jac, bounds = cap.fun, cap.args, cap.constraints, cap.jac, cap.bounds
+    else:
+        from oracle import og_numpy
+        wl = workloads.build(cfg, og_numpy)
+        prob, obj = wl.prob, wl.obj
+        fun, args_, jac, bounds = (lambda x: prob.eval_cost(x, obj)), (), None, prob.bounds
+        cons = ({"type": "eq", "fun": lambda x: prob.eval_equality(x, obj)},
+                {"type": "ineq", "fun": lambda x: prob.eval_inequality(x, obj)})
+    X0 = workloads.make_batch(wl, 2)
+    t0 = time.perf_counter()
+    nit = 0
+    for x0 in X0:
+        with contextlib.redirect_stdout(io.StringIO()):
+            opt = optimize.minimize(fun, x0, args=args_, bounds=bounds, constraints=cons, jac=jac, method="SLSQP",
+                                    options={"disp": False, "maxiter": iters, "ftol": 1e-10})
+        nit += int(opt.nit)
+    wall = time.perf_counter() - t0
+    return {"kind": kind, "cores": 1, "instance_iterations_per_s_per_core": nit / wall,
+            "ms_per_iteration": 1e3 * wall / max(1, nit), "instances": len(X0)}
+
+
 # ------------------------------------------------------------------ the CUDA arm
 def main():
     ap = argparse.ArgumentParser()
@@ -285,6 +501,8 @@ def main():
                     help="keep the sweep kernel's default CTA size (256 threads) instead of timing 256 / 384 / 128 first")
     ap.add_argument("--autotune", action="store_true", help="(default; kept for older command lines)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads of the e2e session (default: cores / ranks)")
+    ap.add_argument("--no-extras", action="store_true", help="skip parity / tensor / latency / sparse / solve extras")
+    ap.add_argument("--solve-starts", type=int, default=256, help="multi-start instances of the solve_batch extra")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg, default_batch = WORKLOADS[args.workload]
@@ -346,6 +564,10 @@ def main():
                 pass
         torch.cuda.empty_cache()
     n, M = eng.nvars, eng.nrows
+    parity = tensor = None
+    if rank == 0 and not args.no_extras:
+        parity = parity_check(eng, cfg, workloads, P_host.numpy()[:3])
+        tensor = tensor_check(eng, wl, P, torch)
     c = torch.empty((B, M), dtype=torch.float64, device=dev)
     J = torch.empty((B, n, M), dtype=torch.float64, device=dev)
     DX = torch.empty((B, eng.ndx), dtype=torch.float64, device=dev)
@@ -388,6 +610,7 @@ def main():
     launches = eng.launches - launches0
     step_ms = [e[0].elapsed_time(e[2]) for e in events]
     sweep_ms = [e[1].elapsed_time(e[2]) for e in events]
+    gemm_ms = [e[0].elapsed_time(e[1]) for e in events]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -467,7 +690,41 @@ def main():
             e2e["dma_error"] = str(ex)[:120]
         e2e["variants"] = var
     launches_e2e = int(st.launches)
+    # ---- the transport the SQP driver really uses (ogb_host_eval_fd_scatter): the packed non-zeros of every
+    #      instance scattered straight into that instance's persistent SLSQP buffers (C: Fortran (m, n), g: (n,)),
+    #      which keep their zero background -- no dense J is rebuilt anywhere.  Bound: PCIe (8 nnz + 8 M bytes
+    #      per eval over the device->host link).
+    e2e_sqp = None
+    try:
+        m = M - 1
+        del hJ
+        Cbuf = np.zeros((B, n, max(1, m)), dtype=np.float64)          # per instance an (m, n) Fortran matrix
+        Gbuf = np.zeros((B, n), dtype=np.float64)
+        Cp = [Cbuf.ctypes.data + b * Cbuf.strides[0] for b in range(B)]
+        Gp = [Gbuf.ctypes.data + b * Gbuf.strides[0] for b in range(B)]
+        sess.eval_fd_scatter(P_host, hc, Cp, max(1, m), m, Gp)        # warm-up (faults the pages in)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sess.eval_fd_scatter(P_host, hc, Cp, max(1, m), m, Gp)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        barrier()
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        st3 = sess.stats()
+        e2e_sqp = {"value": world * B * e2e_steps / float(dt.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(st3.h2d_bytes), "d2h_bytes_per_step": int(st3.d2h_bytes),
+                   "api": "ogb_host_eval_fd_scatter: pinned host p -> H2D -> K1 -> K2a -> D2H of c and the packed "
+                          "non-zeros -> host threads scatter them into B persistent per-instance SLSQP buffers "
+                          "(C (m, n) Fortran + g), zero background kept; host wall clock",
+                   "pcie_bound_evals_per_s_at_55GBs": 55e9 / (8.0 * (st3.nnz + M))}
+        del Cbuf, Gbuf
+    except Exception as ex:
+        e2e_sqp = {"error": str(ex)[:200]}
     sess.close()
+    extra = None
+    if rank == 0 and not args.no_extras:
+        extra = extras(eng, wl, cfg, workloads, P, P_host, torch, args, api)
 
     if rank == 0:
         peaks = {}
@@ -505,7 +762,16 @@ def main():
                          "kernel_ms": sweep_avg_ms, "bytes_per_launch": B * bytes_per_eval,
                          "peak_source": peak_src},
             "cpu_baseline": cpu,
+            "e2e_sqp": e2e_sqp,
+            "parity": parity,
+            "tensor": tensor,
+            "extra": extra,
         }
+        if tensor is not None:
+            k1 = sum(gemm_ms) / len(gemm_ms)
+            tensor["k1_ms_in_step"] = k1
+            tensor["k1_tflops_in_step"] = tensor["flop_per_launch"] / (k1 * 1e-3) / 1e12
+            tensor["frac_in_step"] = tensor["k1_tflops_in_step"] / tensor["dgemm_peak_tflops"]
         if gather is not None:
             out["gather"] = gather
         print(json.dumps(out), flush=True)

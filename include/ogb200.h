@@ -260,7 +260,7 @@ int ogb_guess_fill(void* prob, const ogb_guess_spec* specs_h, int nspec, const d
  *   u ~ U[-1, 1);   then clipped into [lb, ub] (either may be NULL).
  * Counter-based generator (Philox4x32-10, key = seed, counter = (variable, 0, first_instance + b, 0); Box-Muller
  * on two 53-bit uniforms), so any sub-range of instances is reproducible on any number of GPUs; restated
- * in numpy by oracle/og_rng.py for the parity test.                                                    */
+ * in numpy by the test oracle (og_rng) for the parity test.                                                  */
 int ogb_jitter(void* prob, double* P, int B, uint64_t seed, int64_t first_instance, double rel_x, double rel_t,
                const double* lb, const double* ub, void* stream);
 

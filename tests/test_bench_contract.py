@@ -25,9 +25,21 @@ def test_reference_arm_prints_one_json_line():
     assert d["unit"] == "evals/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["scaling"] == "weak" and d["dtype"] == "f64"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    from oracle import ref_loader
+    # the real reference wherever it can be imported (/root/reference here, baseline/_ref on the GPU box)
+    assert cb["kind"] == ("reference" if ref_loader.reference_available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("brachistochrone20")
+
+
+def test_reference_arm_falls_back_to_the_oracle_port():
+    env = dict(os.environ, PYTHONPATH=ROOT, OGB200_CPU_KIND="port")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--workload", "brachistochrone20"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
 
 
 def test_reference_arm_other_ranks_do_no_work():
