@@ -34,7 +34,10 @@ extern "C" {
  * register programs.  One instruction = one 64-bit word:
  *     op[63:56]  dst[55:42]  a[41:28]  b[27:14]  c[13:0]
  * A *node program* runs once per LGL node: OGB_LDP reads block `a` (state or control
- * number within the phase) of the decision vector at that node.  The *scalar
+ * number within the phase) of the decision vector at that node; operands beyond the phase's
+ * blocks address first the program's per-node constant vectors (nodec_h: e.g. prob.time[s],
+ * reference optimize.py:786-791), then its global variables (globals_h: final times read at
+ * every node, optimize.py:349-360 -- non-autonomous dynamics).  The *scalar
  * program* runs once per decision vector: OGB_LDP reads variable `a` of p.          */
 enum ogb_opcode {
     OGB_NOP = 0,
@@ -93,6 +96,9 @@ typedef struct ogb_program {
     const double*   consts_h; int32_t nconsts;
     const ogb_out*  outs_h;   int32_t nouts;   /* slot i of OGB_OUT <-> outs_h[i] */
     int32_t nreg;
+    const double*   nodec_h;  int32_t n_nodec; /* node programs: n_nodec vectors of `nodes` doubles (operand nb + i) */
+    const int32_t*  globals_h; int32_t nglobals; /* node programs: final-time variable indices (operand nb + n_nodec + i);
+                                                  the Jacobian columns of these variables are dense in the phase  */
 } ogb_program;
 
 /* Everything `Problem.__init__` + the unit setters + the traced callbacks define
@@ -177,6 +183,8 @@ enum ogb_option {
                                     Results are bit-identical either way.                                         */
     OGB_OPT_SPLIT_CHUNK = 10,    /* instances per chunk of the split pipeline (0 = auto, ~192 MB of dense J)        */
     OGB_OPT_DENSE_STREAMING = 11,/* 1 (default): K2b writes its zeros with st.global.cs (evict-first)              */
+    OGB_OPT_ZERO_MODE = 12,      /* experiments on the fused kernel's zero stream (results unchanged): bit 0 = st.global.cs
+                                    stores, bit 1 = the CTA fills the item's whole region first, then scatters     */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
                                     launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
                                     (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */

@@ -22,7 +22,9 @@ class OgbProgram(C.Structure):
     _fields_ = [("code_h", C.POINTER(C.c_uint64)), ("ncode", C.c_int32),
                 ("consts_h", C.POINTER(C.c_double)), ("nconsts", C.c_int32),
                 ("outs_h", C.POINTER(OgbOut)), ("nouts", C.c_int32),
-                ("nreg", C.c_int32)]
+                ("nreg", C.c_int32),
+                ("nodec_h", C.POINTER(C.c_double)), ("n_nodec", C.c_int32),
+                ("globals_h", C.POINTER(C.c_int32)), ("nglobals", C.c_int32)]
 
 
 class OgbTable(C.Structure):
@@ -83,10 +85,16 @@ def _program(tape, keep):
     outs = (OgbOut * max(1, len(tape.outs)))()
     for i, (kind, row, glo, ghi) in enumerate(tape.outs):
         outs[i] = OgbOut(kind, row, glo, ghi)
-    keep.extend([code, consts, outs])
+    nodec = getattr(tape, "nodec", None) or []
+    gl = getattr(tape, "globals", None) or []
+    ncv = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in nodec]) if nodec else np.zeros(1))
+    glv = np.ascontiguousarray(gl if gl else [0], dtype=np.int32)
+    keep.extend([code, consts, outs, ncv, glv])
     return OgbProgram(code.ctypes.data_as(C.POINTER(C.c_uint64)), len(code),
                       consts.ctypes.data_as(C.POINTER(C.c_double)), len(tape.consts),
-                      outs, len(tape.outs), tape.nreg)
+                      outs, len(tape.outs), tape.nreg,
+                      ncv.ctypes.data_as(C.POINTER(C.c_double)), len(nodec),
+                      glv.ctypes.data_as(C.POINTER(C.c_int32)), len(gl))
 
 
 def make_desc(ir):

@@ -44,6 +44,8 @@ struct OgbSec {
     int us_off;             // offset into the concatenated unit_states
     int code_off, ncode, const_off, out_off, nouts, nreg;   // node program
     int run_slot;           // output slot carrying the running-cost integrand, -1 = none
+    int nnc, ncoff;         // per-node constant vectors of the node program: count, offset into P.nodec (N doubles each)
+    int ng, goff;           // global variables (final times) the node program reads: count, offset into P.gvars
     int pad;
 };
 #ifdef OGB_SPEC_SECTIONS               // NVRTC build: the records are a constant table (see ogb_sec)
@@ -64,6 +66,9 @@ struct OgbCol {             // how Jacobian column j is produced
 
 struct OgbProb {
     int nsec, n, M, meq, mineq, ndx, gtot, nknot, npick, has_running, max_nouts;
+    int any_global;         // some node program reads a final time: those columns recompute whole phases
+    const double* nodec;    // per-node constant vectors of the node programs
+    const int* gvars;       // global variable indices of the node programs
     int sc_code_off, sc_ncode, sc_const_off, sc_out_off, sc_nouts, sc_nreg, sc_cost_slot;
     double unit_time, t0x;  // t0x = time_start(0) / unit_time (optimize.py:683)
     const OgbSec* sec;
@@ -109,6 +114,8 @@ struct OgbWork {            // per work item scratch (shared memory on the devic
     double* rterm;          // [gtot] running-cost terms integrand * w at the base point
     double* costp;          // [G] cost at the perturbed point of each column
     double* prdx;           // [G] 1 / dx, correctly rounded (see ogb_fd_div)
+    double* gpert;          // [nsec][max_nouts][gtot] (only if P.any_global) node-program outputs at every node with
+                            // final time t perturbed (FD) / their tangents (exact), for the phases that read it
     int G;
 };
 
@@ -124,7 +131,7 @@ struct OgbPlan {
     int ctas_per_sm;
     // offsets (in doubles) into the dynamic shared memory block
     unsigned long long o_cache, o_sp, o_sdx, o_sbase, o_sc, o_scbase, o_coef, o_prefix, o_pert, o_pdx, o_px1,
-        o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_prdx, o_slot, o_tiles, tile_stride, o_tail,
+        o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_prdx, o_slot, o_gpert, o_tiles, tile_stride, o_tail,
         tail_stride, o_end;
 };
 
@@ -203,13 +210,36 @@ OGB_HD double ogb_fd_step(double x0, double lb, double ub, double abs_step) {
 }
 
 // ------------------------------------------------------------------ tape interpreter
-struct OgbNodeLoad {        // node program input: block `a` of the phase at one node
+struct OgbNodeLoad {        // node program input `a` at one node: a block of the phase, a per-node constant, a global
     const double* at;       // &sp[off + k]
     int N;
     int pblk;               // perturbed block, -1 = none
     double x1;
-    OGB_HD double operator()(int a) const { return a == pblk ? x1 : at[a * N]; }
+    int nb, nnc;            // blocks of the phase, per-node constant vectors of the program
+    const double* cat;      // &nodec[ncoff + k]
+    const int* gv;          // the program's global variable indices
+    const double* sp;
+    int pg;                 // perturbed global (index into gv), -1 = none
+    double gx1;
+    OGB_HD double operator()(int a) const {
+        if (a < nb) return a == pblk ? x1 : at[a * N];
+        a -= nb;
+        if (a < nnc) return cat[a * N];
+        a -= nnc;
+        return a == pg ? gx1 : sp[gv[a]];
+    }
 };
+// the loader of phase S at node k (pblk / x1: a perturbed block; pg / gx1: a perturbed global)
+OGB_HD OgbNodeLoad ogb_node_load(const OgbProb& P, const double* sp, const OgbSec& S, int k, int pblk, double x1,
+                                 int pg = -1, double gx1 = 0.0) {
+    return OgbNodeLoad{sp + S.off + k, S.N, pblk, x1, S.nb, S.nnc, P.nodec + S.ncoff + k, P.gvars + S.goff, sp, pg, gx1};
+}
+// which of phase S's globals is variable j (-1: the phase does not read it)
+OGB_HD int ogb_global_slot(const OgbProb& P, const OgbSec& S, int j) {
+    for (int t = 0; t < S.ng; ++t)
+        if (P.gvars[S.goff + t] == j) return t;
+    return -1;
+}
 
 struct OgbScalarLoad {      // scalar program input: variable `a` of p
     const double* sp;
@@ -528,15 +558,22 @@ __device__ __forceinline__ void ogb_jit_scalar_dual(const OgbProb& P, const Load
 #endif
 
 // ------------------------------------------------------------------ phase 2: tape jobs
+// Number of tape jobs of a work item with ncols Jacobian columns (see ogb_job).
+OGB_HD int ogb_njobs(const OgbProb& P, int ncols) {
+    return P.gtot + 1 + ncols + ((ncols > 0 && P.any_global) ? P.nsec * P.gtot : 0);
+}
+
 // Job q of a work item: q < gtot: node program at base node q; q == gtot: scalar program
-// at the base point + the per-phase time coefficients; q > gtot: Jacobian column
-// jlo + (q - gtot - 1): FD step, perturbed node program, perturbed scalar program.
-OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
+// at the base point + the per-phase time coefficients; gtot < q <= gtot + ncols: Jacobian column
+// jlo + (q - gtot - 1): FD step, perturbed node program, perturbed scalar program; beyond (only when a node
+// program reads a final time): job (t, g) = the node program at node g with final time t perturbed, for the
+// dense column of that final time.
+OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo, int ncols,
                     const double* lb, const double* ub, double abs_step) {
     if (q < P.gtot) {
         const int s = ogb_sec_of_node(P, q);
         const OgbSec& S = ogb_sec(P, s);
-        OgbNodeLoad ld{W.sp + S.off + (q - S.g0), S.N, -1, 0.0};
+        const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, q - S.g0, -1, 0.0);
         OGB_NODE_PROGRAM(s, S, ld, W.sbase + q, P.gtot);
     } else if (q == P.gtot) {
         OgbScalarLoad ld{W.sp, -1, 0.0};
@@ -549,7 +586,7 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
             W.coef[3 * s + 1] = tfx;
             W.coef[3 * s + 2] = tix;
         }
-    } else {
+    } else if (q <= P.gtot + ncols) {
         const int cl = q - P.gtot - 1;
         const int j = jlo + cl;
         const double x0 = W.sp[j];
@@ -567,7 +604,7 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
                 const double u = P.ustate[S.us_off + col.blk];
                 dlt = ogb_nd(x1, u) - ogb_nd(x0, u);
             }
-            OgbNodeLoad ld{W.sp + S.off + col.k, S.N, col.blk, x1};
+            const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, col.k, col.blk, x1);
             OGB_NODE_PROGRAM(col.sec, S, ld, W.pert + cl, W.G);
         }
         W.pdlt[cl] = dlt;
@@ -575,6 +612,19 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo,
             OgbScalarLoad ld{W.sp, j, x1};
             OGB_SCALAR_PROGRAM(ld, W.scpert + col.pick, P.npick);
         }
+    } else {
+        const int e = q - (P.gtot + 1 + ncols);
+        const int t = e / P.gtot, g = e - t * P.gtot;
+        const int j = ogb_sec(P, t).tf_idx;
+        if (j < jlo || j >= jlo + ncols) return;      // that column belongs to another work item
+        const int s = ogb_sec_of_node(P, g);
+        const OgbSec& S = ogb_sec(P, s);
+        const int slot = ogb_global_slot(P, S, j);
+        if (slot < 0) return;
+        const double x0 = W.sp[j];
+        const double x1 = x0 + ogb_fd_step(x0, lb[j], ub[j], abs_step);
+        const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, g - S.g0, -1, 0.0, slot, x1);
+        OGB_NODE_PROGRAM(s, S, ld, W.gpert + (size_t)t * P.max_nouts * P.gtot + g, P.gtot);
     }
 }
 
@@ -637,7 +687,7 @@ OGB_HD void ogb_assemble_cost(const OgbProb& P, const OgbWork& W) {
 // part from the perturbed scalar program if the variable is picked, the running sum redone
 // left to right with the one changed term so the rounding matches the reference's sum().
 OGB_HD bool ogb_col_moves_cost(const OgbProb& P, const OgbCol& cd) {
-    return cd.pick >= 0 || (P.has_running && cd.sec >= 0);
+    return cd.pick >= 0 || (P.has_running && (cd.sec >= 0 || P.any_global));
 }
 OGB_HD void ogb_cost_column(const OgbProb& P, const OgbWork& W, int cl) {
     const OgbCol cd = W.pcol[cl];
@@ -650,6 +700,17 @@ OGB_HD void ogb_cost_column(const OgbProb& P, const OgbWork& W, int cl) {
             const int g = S.g0 + cd.k;
             acc = W.prefix[g] + W.pert[S.run_slot * W.G + cl] * P.w[g];
             for (int g2 = g + 1; g2 < P.gtot; ++g2) acc += W.rterm[g2];
+        } else if (P.any_global) {
+            // a final time the integrand may read: the whole sum again, left to right, with the re-evaluated
+            // terms of the phases that read it
+            const int t = cd.blk, j = ogb_sec(P, t).tf_idx;
+            acc = 0.0;
+            for (int s = 0; s < P.nsec; ++s) {
+                const OgbSec& S = ogb_sec(P, s);
+                const bool reads = ogb_global_slot(P, S, j) >= 0;
+                const double* gp = W.gpert + ((size_t)t * P.max_nouts + S.run_slot) * P.gtot;
+                for (int g = S.g0; g < S.g0 + S.N; ++g) acc += reads ? gp[g] * P.w[g] : W.rterm[g];
+            }
         }
         cost = cost + acc;
     }
@@ -732,21 +793,38 @@ OGB_HD void ogb_scatter_knots(const OgbProb& P, const OgbWork& W, int j, double 
     }
 }
 
-// a final-time variable: the defects of its own phase and of the next one rescale
+// a final-time variable: the defects of its own phase and of the next one rescale; phases whose node program
+// reads it (non-autonomous dynamics, time-dependent path rows) are re-evaluated at every node (W.gpert)
 template <class Out>
 OGB_HD void ogb_scatter_time(const OgbProb& P, const OgbWork& W, int j, int sec, double x1, double dx,
                              double rdx, const Out& col, int lane, int nlanes) {
     const double tfx1 = ogb_nd(x1, P.unit_time);
-    for (int s = sec; s < P.nsec && s <= sec + 1; ++s) {
+    const int slo = P.any_global ? 0 : sec, shi = P.any_global ? P.nsec : (sec + 2 < P.nsec ? sec + 2 : P.nsec);
+    for (int s = slo; s < shi; ++s) {
         const OgbSec& S = ogb_sec(P, s);
-        double coef1;
-        if (s == sec) coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0;
-        else if (S.t0_idx == j) coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0;
-        else continue;
+        const bool reads = P.any_global && ogb_global_slot(P, S, j) >= 0;
+        double coef1 = W.coef[3 * s];
+        bool moved = reads;
+        if (s == sec) { coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0; moved = true; }
+        else if (S.t0_idx == j) { coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0; moved = true; }
+        if (!moved) continue;
+        const double* f1 = reads ? W.gpert + (size_t)sec * P.max_nouts * P.gtot : W.sbase;
         for (int e = lane; e < S.ns * S.N; e += nlanes) {
             const int b = e / S.N, i = e - b * S.N;
-            const double cp = W.sdx[S.dxoff + e] - coef1 * W.sbase[b * P.gtot + S.g0 + i];
+            const double cp = W.sdx[S.dxoff + e] - coef1 * f1[b * P.gtot + S.g0 + i];
             col.put(S.rdef + e, ogb_fd_div(cp - W.sc[S.rdef + e], dx, rdx));
+        }
+        if (!reads) continue;
+        for (int slot = S.ns; slot < S.nouts; ++slot) {          // pointwise user rows that read the final time
+            const ogb_out o = P.outs[S.out_off + slot];
+            if (o.kind != OGB_OUT_EQ_POINT && o.kind != OGB_OUT_INEQ_POINT) continue;
+            for (int k = lane; k < S.N; k += nlanes) {
+                const int g = S.g0 + k;
+                if (g >= o.glo && g < o.ghi) {
+                    const int r = o.row + (g - o.glo);
+                    col.put(r, ogb_fd_div(f1[slot * P.gtot + g] - W.sc[r], dx, rdx));
+                }
+            }
         }
     }
 }
@@ -797,21 +875,34 @@ OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl
 // traced tapes run in dual arithmetic (ogb_run_tape_dual / the NVRTC-generated dual programs).
 
 // Job q of a work item in exact mode: q <= gtot as in ogb_job; q > gtot: tangents of column jlo + (q - gtot - 1)
-OGB_HD void ogb_job_exact(const OgbProb& P, const OgbWork& W, int q, int jlo) {
-    if (q <= P.gtot) { ogb_job(P, W, q, jlo, nullptr, nullptr, 0.0); return; }
-    const int cl = q - P.gtot - 1;
-    const int j = jlo + cl;
-    const OgbCol col = P.cols[j];
-    W.pcol[cl] = col;
-    if (col.sec >= 0) {
-        const OgbSec& S = ogb_sec(P, col.sec);
-        OgbNodeLoad ld{W.sp + S.off + col.k, S.N, -1, 0.0};
-        OGB_NODE_PROGRAM_DUAL(col.sec, S, ld, col.blk, W.pert + cl, W.G);
+OGB_HD void ogb_job_exact(const OgbProb& P, const OgbWork& W, int q, int jlo, int ncols) {
+    if (q <= P.gtot) { ogb_job(P, W, q, jlo, ncols, nullptr, nullptr, 0.0); return; }
+    if (q <= P.gtot + ncols) {
+        const int cl = q - P.gtot - 1;
+        const int j = jlo + cl;
+        const OgbCol col = P.cols[j];
+        W.pcol[cl] = col;
+        if (col.sec >= 0) {
+            const OgbSec& S = ogb_sec(P, col.sec);
+            const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, col.k, -1, 0.0);
+            OGB_NODE_PROGRAM_DUAL(col.sec, S, ld, col.blk, W.pert + cl, W.G);
+        }
+        if (col.pick >= 0) {
+            OgbScalarLoad ld{W.sp, -1, 0.0};
+            OGB_SCALAR_PROGRAM_DUAL(ld, j, W.scpert + col.pick, P.npick);
+        }
+        return;
     }
-    if (col.pick >= 0) {
-        OgbScalarLoad ld{W.sp, -1, 0.0};
-        OGB_SCALAR_PROGRAM_DUAL(ld, j, W.scpert + col.pick, P.npick);
-    }
+    const int e = q - (P.gtot + 1 + ncols);              // tangents with respect to a final time, at every node
+    const int t = e / P.gtot, g = e - t * P.gtot;
+    const int j = ogb_sec(P, t).tf_idx;
+    if (j < jlo || j >= jlo + ncols) return;
+    const int s = ogb_sec_of_node(P, g);
+    const OgbSec& S = ogb_sec(P, s);
+    const int slot = ogb_global_slot(P, S, j);
+    if (slot < 0) return;
+    const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, g - S.g0, -1, 0.0);
+    OGB_NODE_PROGRAM_DUAL(s, S, ld, S.nb + S.nnc + slot, W.gpert + (size_t)t * P.max_nouts * P.gtot + g, P.gtot);
 }
 
 // d cost / d x_j of column cl (one thread per column)
@@ -822,6 +913,14 @@ OGB_HD void ogb_cost_column_exact(const OgbProb& P, const OgbWork& W, int cl) {
     if (P.has_running && cd.sec >= 0) {
         const OgbSec& S = ogb_sec(P, cd.sec);
         g = g + W.pert[S.run_slot * W.G + cl] * P.w[S.g0 + cd.k];
+    } else if (P.has_running && P.any_global) {
+        const int t = cd.blk, j = ogb_sec(P, t).tf_idx;
+        for (int s = 0; s < P.nsec; ++s) {
+            const OgbSec& S = ogb_sec(P, s);
+            if (ogb_global_slot(P, S, j) < 0) continue;
+            const double* gp = W.gpert + ((size_t)t * P.max_nouts + S.run_slot) * P.gtot;
+            for (int q = S.g0; q < S.g0 + S.N; ++q) g = g + gp[q] * P.w[q];
+        }
     }
     W.costp[cl] = g;
 }
@@ -858,15 +957,30 @@ OGB_HD void ogb_scatter_column_exact(const OgbProb& P, const OgbWork& W, int j, 
         }
     } else {
         const int sec = cd.blk;
-        for (int s = sec; s < P.nsec && s <= sec + 1; ++s) {
+        const int slo = P.any_global ? 0 : sec, shi = P.any_global ? P.nsec : (sec + 2 < P.nsec ? sec + 2 : P.nsec);
+        for (int s = slo; s < shi; ++s) {
             const OgbSec& S = ogb_sec(P, s);
-            double sign;
+            const bool reads = P.any_global && ogb_global_slot(P, S, j) >= 0;
+            double sign = 0.0;                           // -d coef_s / d t_f
             if (s == sec) sign = -0.5;
             else if (S.t0_idx == j) sign = 0.5;
-            else continue;
+            else if (!reads) continue;
+            const double coef = W.coef[3 * s];
+            const double* tg = W.gpert + (size_t)sec * P.max_nouts * P.gtot;     // tangents, if the phase reads t_f
             for (int e = lane; e < S.ns * S.N; e += nlanes) {
                 const int b = e / S.N, i = e - b * S.N;
-                col.put(S.rdef + e, sign * W.sbase[b * P.gtot + S.g0 + i]);
+                double v = sign * W.sbase[b * P.gtot + S.g0 + i];
+                if (reads) v = v - coef * tg[b * P.gtot + S.g0 + i];
+                col.put(S.rdef + e, v);
+            }
+            if (!reads) continue;
+            for (int slot = S.ns; slot < S.nouts; ++slot) {
+                const ogb_out o = P.outs[S.out_off + slot];
+                if (o.kind != OGB_OUT_EQ_POINT && o.kind != OGB_OUT_INEQ_POINT) continue;
+                for (int k = lane; k < S.N; k += nlanes) {
+                    const int g = S.g0 + k;
+                    if (g >= o.glo && g < o.ghi) col.put(o.row + (g - o.glo), tg[slot * P.gtot + g]);
+                }
             }
         }
     }

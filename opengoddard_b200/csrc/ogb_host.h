@@ -21,7 +21,8 @@ struct OgbHostProblem {
     std::vector<OgbSec> sec;
     std::vector<ogb_out> outs;
     std::vector<uint64_t> code;
-    std::vector<double> consts, D, Dt, w, tau, ustate, ucontrol;
+    std::vector<double> consts, D, Dt, w, tau, ustate, ucontrol, nodec;
+    std::vector<int> gvars;
     std::vector<OgbKnot> knots;
     std::vector<OgbCol> cols;
     std::vector<int> pickvars;
@@ -36,6 +37,7 @@ struct OgbHostProblem {
         P.sec = sec.data(); P.outs = outs.data(); P.code = code.data(); P.consts = consts.data();
         P.D = D.data(); P.Dt = Dt.data(); P.w = w.data(); P.ustate = ustate.data();
         P.tau = tau.data(); P.ucontrol = ucontrol.data();
+        P.nodec = nodec.data(); P.gvars = gvars.data();
         P.knots = knots.data(); P.cols = cols.data(); P.pickvars = pickvars.data();
         P.tables = tables.data(); P.tab_x = tab_x.data(); P.tab_y = tab_y.data();
     }
@@ -93,6 +95,7 @@ static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, si
     pl->o_costp = o;   o += ogb_even(pl->G);
     pl->o_prdx = o;    o += ogb_even(pl->G);
     pl->o_slot = o;    o += nouts * 2;                     // int4 per output slot
+    pl->o_gpert = o;   o += P.any_global ? ogb_even((size_t)P.nsec * P.max_nouts * P.gtot) : 0;
     pl->o_tiles = pl->o_tail = o;                          // (no column staging: J is written directly)
     pl->tile_stride = pl->tail_stride = 0;
     pl->o_end = o;
@@ -280,8 +283,18 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
             if (o.kind == OGB_OUT_RUNNING) S.run_slot = i;
             if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR || o.kind == OGB_OUT_COST) { delete H; return fail("scalar output kind in a node program"); }
         }
+        if (pr.n_nodec < 0 || pr.nglobals < 0 || (pr.n_nodec > 0 && !pr.nodec_h) || (pr.nglobals > 0 && !pr.globals_h)) { delete H; return fail("bad node-constant / global tables of a node program"); }
+        S.nnc = pr.n_nodec; S.ncoff = (int)H->nodec.size();
+        H->nodec.insert(H->nodec.end(), pr.nodec_h, pr.nodec_h + (size_t)pr.n_nodec * S.N);
+        S.ng = pr.nglobals; S.goff = (int)H->gvars.size();
+        for (int i = 0; i < pr.nglobals; ++i) {
+            const int v = pr.globals_h[i];
+            if (v < P.n - d->nsec || v >= P.n) { delete H; return fail("a node program may only read final times as global variables"); }
+            H->gvars.push_back(v);
+        }
+        if (pr.nglobals > 0) P.any_global = 1;
         for (int i = 0; i < pr.ncode; ++i)
-            if ((int)(pr.code_h[i] >> 56) == OGB_LDP && (int)((pr.code_h[i] >> 28) & 0x3fff) >= S.nb) { delete H; return fail("node program reads a block outside the phase"); }
+            if ((int)(pr.code_h[i] >> 56) == OGB_LDP && (int)((pr.code_h[i] >> 28) & 0x3fff) >= S.nb + S.nnc + S.ng) { delete H; return fail("node program reads an input outside the phase's blocks, constants and globals"); }
         if (d->has_running_cost && S.run_slot < 0) { delete H; return fail("running cost declared but a phase has no integrand output"); }
         P.max_nouts = std::max(P.max_nouts, pr.nouts);
     }
@@ -316,6 +329,8 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
     }
     for (int i = 0; i < P.npick; ++i) H->cols[H->pickvars[i]].pick = i;
     if (H->pickvars.empty()) H->pickvars.push_back(0);   // keep the device array non-empty
+    if (H->nodec.empty()) H->nodec.push_back(0.0);
+    if (H->gvars.empty()) H->gvars.push_back(0);
 
     H->bind_host();
     if (!ogb_make_plan(P, H->code.size(), H->consts.size(), H->outs.size(), &H->plan, err)) { delete H; return nullptr; }

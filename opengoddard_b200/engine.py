@@ -280,7 +280,7 @@ class DeviceProblem:
             cache[bool(exact)] = _HostEvaluator(self, exact=bool(exact))
         return cache[bool(exact)]
 
-    def autotune(self, P, candidates=(256, 384, 128), min_gain=0.02, reps=5):
+    def autotune(self, P, candidates=(256, 384, 128), min_gain=0.03, reps=5):
         """Pick the CTA size of the NVRTC-specialised sweep kernel by timing ogb_sweep on the batch
         P (device or host array): wide CTAs (12 warps) finish the tape phase of problems with heavy
         dynamics in one round instead of two (polar 3 x 40: 0.60 -> 0.56 ms), narrow ones keep more

@@ -453,7 +453,8 @@ class Problem:
         reach exit mode 0 are restarted from where they stopped, up to `max_outer`
         (default maxIterator) times.  `processes` > 1 steps the per-instance SLSQP cores in that many
         worker processes (SciPy's step holds the GIL, so this is what makes the host side scale with
-        the cores; sqp._ProcessStepper).  jacobian="exact": SLSQP is given the exact Jacobians (opt-in; the
+        the cores; sqp._ProcessStepper); a sqp.WorkerPool instance is used as is and left running, so
+        repeated calls do not pay for starting the workers.  jacobian="exact": SLSQP is given the exact Jacobians (opt-in; the
         reference's are forward differences).  Returns dict(x, fun, status, nit, outer)."""
         from . import batch, sqp
         self._check_callbacks()
@@ -479,7 +480,11 @@ class Problem:
             def grad(x):
                 self.p = x
                 return np.ascontiguousarray(self.cost_derivative(self, obj), dtype=np.float64)
-        pool = sqp.WorkerPool(min(int(processes), B)) if processes and processes > 1 and B > 1 else None
+        own_pool = not isinstance(processes, sqp.WorkerPool)
+        if own_pool:
+            pool = sqp.WorkerPool(min(int(processes), B)) if processes and processes > 1 and B > 1 else None
+        else:
+            pool = processes                                # the caller's pool (kept alive across solve_batch calls)
         try:                                                # one set of worker processes for all outer passes
             for _ in range(self.maxIterator if max_outer is None else max_outer):
                 ids = np.nonzero(status != 0)[0]
@@ -494,7 +499,7 @@ class Problem:
                 nit[ids] += res["nit"]
                 outer[ids] += 1
         finally:
-            if pool is not None:
+            if pool is not None and own_pool:
                 pool.close()
         return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
 

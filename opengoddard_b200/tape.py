@@ -21,6 +21,7 @@ OPCODES = {
     "cosh": 33, "tanh": 34, "log10": 35, "sign": 36, "floor": 37, "ceil": 38, "and": 39,
     "or": 40, "not": 41, "interp": 42,
 }
+LEAF_OPS = ("blk", "var", "const", "nodec")
 MAX_REG = 96
 MAX_FIELD = 16383
 
@@ -40,6 +41,10 @@ class Tape:
     consts: np.ndarray          # float64
     outs: list                  # [(kind, row, glo, ghi)] ; slot i <-> outs[i]
     nreg: int
+    # node programs only: LDP operand a addresses block a (a < nb), then per-node constant vector a - nb,
+    # then global variable a - nb - len(nodec) (a final time read at every node)
+    nodec: list = field(default_factory=list)       # arrays of one value per node of the phase
+    globals: list = field(default_factory=list)     # decision-variable indices
 
 
 def compile_tape(out_nodes, outs, leaf_arg):
@@ -58,14 +63,14 @@ def compile_tape(out_nodes, outs, leaf_arg):
                 continue
             seen.add(n.uid)
             stack.append((n, True))
-            for a in reversed(n.args if n.op not in ("blk", "var", "const") else ()):
+            for a in reversed(n.args if n.op not in LEAF_OPS else ()):
                 if a.uid not in seen:
                     stack.append((a, False))
     pos = {n.uid: i for i, n in enumerate(order)}
     # ---- last use (outputs are emitted right after their node is available: see below)
     last = {n.uid: pos[n.uid] for n in order}
     for n in order:
-        if n.op not in ("blk", "var", "const"):
+        if n.op not in LEAF_OPS:
             for a in n.args:
                 last[a.uid] = max(last[a.uid], pos[n.uid])
     out_slots = {}
@@ -76,8 +81,8 @@ def compile_tape(out_nodes, outs, leaf_arg):
     reg, free, nreg = {}, [], 0
     for i, n in enumerate(order):
         # operands whose last use is this instruction can donate their register
-        srcs = [reg[a.uid] for a in n.args] if n.op not in ("blk", "var", "const") else []
-        for a in (n.args if n.op not in ("blk", "var", "const") else ()):
+        srcs = [reg[a.uid] for a in n.args] if n.op not in LEAF_OPS else []
+        for a in (n.args if n.op not in LEAF_OPS else ()):
             if last[a.uid] == i and a.uid in reg:
                 r = reg.pop(a.uid)
                 free.append(r)
@@ -93,7 +98,7 @@ def compile_tape(out_nodes, outs, leaf_arg):
                 cindex[key] = len(consts)
                 consts.append(n.value)
             code.append(_word(OPCODES["ldc"], d, cindex[key]))
-        elif n.op in ("blk", "var"):
+        elif n.op in ("blk", "var", "nodec"):
             code.append(_word(OPCODES["ldp"], d, leaf_arg(n)))
         elif n.op == "interp":
             code.append(_word(OPCODES["interp"], d, srcs[0], int(n.value)))
@@ -130,6 +135,14 @@ class ProblemIR:
     unit_controls: list = field(default_factory=list)   # flattened over phases (guess / trajectory kernels only)
 
 
+def _node_local(ctx, leaf, s):
+    """May a node program of phase s read this leaf?  The phase's own blocks and per-node constants at the
+    node, and the final times (global: every node reads the same value; their Jacobian columns are dense)."""
+    if leaf[0] in ("blk", "nodec"):
+        return leaf[1] == s
+    return leaf[0] == "var" and ctx.is_time_var(leaf[1])
+
+
 class _RowBuilder:
     """Turns the ordered pieces of a traced Condition into output slots."""
 
@@ -149,7 +162,7 @@ class _RowBuilder:
             if piece.rng is None:
                 self._scalar(piece.parts)
                 return
-            local = all(all(l[0] == "blk" and l[1] == s for l in T.leaves(p))
+            local = all(all(_node_local(self.ctx, l, s) for l in T.leaves(p))
                         for s, p in piece.parts.items())
             if local:
                 glo, ghi = piece.rng
@@ -201,6 +214,9 @@ def _build_ir(prob, obj):
             raise T.TraceError("dynamics of phase %d returned %d states, expected %d"
                                % (s, len(items), ctx.nstates[s]))
         for a, it in enumerate(items):
+            if isinstance(it, T.SymList):
+                raise T.TraceError("dynamics[%d] of phase %d mixes nodes (a reversed / shifted vector, or vectors of "
+                                   "different node ranges): on the device a dynamics function is evaluated node by node" % (a, s))
             if isinstance(it, T.Sym):
                 if it.rng is None:
                     node = it.parts
@@ -209,15 +225,19 @@ def _build_ir(prob, obj):
                 else:
                     raise T.TraceError("dynamics[%d] of phase %d is not a vector over that phase's nodes" % (a, s))
                 for lf in T.leaves(node):
-                    if lf[0] != "blk" or lf[1] != s:
-                        raise T.TraceError("dynamics of phase %d reads %r: only that phase's states/"
-                                           "controls at the same node are supported on the device" % (s, lf))
+                    if not _node_local(ctx, lf, s):
+                        raise T.TraceError("dynamics of phase %d reads %r: on the device a dynamics function may read "
+                                           "that phase's states / controls at the same node, per-node constants "
+                                           "(prob.time[s], prob.tau[s], tables of one value per node) and the final "
+                                           "times -- not other nodes or phases" % (s, lf))
             else:
                 arr = np.atleast_1d(np.asarray(it, dtype=float))
-                if not np.all(arr == arr.flat[0]):
-                    raise T.TraceError("dynamics[%d] is a non-uniform constant array (per-node data "
-                                       "tables are not supported on the device)" % a)
-                node = g.const(float(arr.flat[0]))
+                if np.all(arr == arr.flat[0]):
+                    node = g.const(float(arr.flat[0]))
+                elif arr.shape == (ctx.nodes[s],):          # a per-node data table as the right-hand side
+                    node = g.nodec(s, ctx.node_const(s, arr))
+                else:
+                    raise T.TraceError("dynamics[%d] of phase %d is a constant array that is not one value per node" % (a, s))
             rhs.append(node)
         dyn_nodes.append(rhs)
 
@@ -246,7 +266,7 @@ def _build_ir(prob, obj):
             raise T.TraceError("running_cost() must return one value per node of every phase")
         for s, p in rres.parts.items():
             for lf in T.leaves(p):
-                if lf[0] != "blk" or lf[1] != s:
+                if not _node_local(ctx, lf, s):
                     raise T.TraceError("running_cost() must be pointwise in the node")
         run_parts = rres.parts
 
@@ -262,7 +282,19 @@ def _build_ir(prob, obj):
         if run_parts is not None:
             nodes_out.append(run_parts[s])
             outs.append((OUT_RUNNING, 0, 0, 0))
-        node_tapes.append(compile_tape(nodes_out, outs, lambda n: n.args[1]))
+        nb, nnc = ctx.nstates[s] + ctx.ncontrols[s], len(ctx.node_consts[s])
+        gvars = sorted({lf[1] for nd in nodes_out for lf in T.leaves(nd) if lf[0] == "var"})
+
+        def leaf_arg(n, nb=nb, nnc=nnc, gvars=gvars):
+            if n.op == "blk":
+                return n.args[1]
+            if n.op == "nodec":
+                return nb + n.args[1]
+            return nb + nnc + gvars.index(n.args[0])
+        tp = compile_tape(nodes_out, outs, leaf_arg)
+        tp.nodec = [np.asarray(v, dtype=np.float64) for v in ctx.node_consts[s]]
+        tp.globals = list(gvars)
+        node_tapes.append(tp)
     sc_nodes = [n for n, _ in eq.scalar] + [n for n, _ in ineq.scalar] + [cost_node]
     sc_outs = [d for _, d in eq.scalar] + [d for _, d in ineq.scalar] + [(OUT_COST, 0, 0, 0)]
     for n in sc_nodes:
@@ -301,6 +333,9 @@ def ir_to_arrays(ir):
         out[name + "_consts"] = np.asarray(tp.consts, dtype=np.float64)
         out[name + "_outs"] = np.array(tp.outs, dtype=np.int64).reshape(-1, 4)
         out[name + "_nreg"] = np.array([tp.nreg], dtype=np.int64)
+        out[name + "_nodec"] = (np.array(tp.nodec, dtype=np.float64).reshape(len(tp.nodec), -1) if len(tp.nodec)
+                                else np.zeros((0, 0)))
+        out[name + "_globals"] = np.array(tp.globals, dtype=np.int64)
     for i, t in enumerate(ir.tables):
         out["table%d_x" % i] = np.asarray(t["x"], dtype=np.float64)
         out["table%d_y" % i] = np.asarray(t["y"], dtype=np.float64)
@@ -312,9 +347,13 @@ def ir_to_arrays(ir):
 def ir_from_arrays(d):
     """Inverse of ir_to_arrays (d: a dict or an open .npz)."""
     def tp(name):
-        return Tape(np.asarray(d[name + "_code"], dtype=np.uint64), np.asarray(d[name + "_consts"], dtype=np.float64),
-                    [tuple(int(v) for v in row) for row in np.asarray(d[name + "_outs"]).reshape(-1, 4)],
-                    int(d[name + "_nreg"][0]))
+        t = Tape(np.asarray(d[name + "_code"], dtype=np.uint64), np.asarray(d[name + "_consts"], dtype=np.float64),
+                 [tuple(int(v) for v in row) for row in np.asarray(d[name + "_outs"]).reshape(-1, 4)],
+                 int(d[name + "_nreg"][0]))
+        if name + "_nodec" in d:
+            t.nodec = [np.asarray(v, dtype=np.float64) for v in np.asarray(d[name + "_nodec"])]
+            t.globals = [int(v) for v in d[name + "_globals"]]
+        return t
     layout = np.asarray(d["layout"])
     flags = [int(v) for v in d["flags"]]
     tables = []

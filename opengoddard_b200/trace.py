@@ -74,6 +74,10 @@ class Graph:
     def var(self, index):
         return self._intern("var", (index,))
 
+    def nodec(self, section, cid):
+        """per-node constant vector `cid` of phase `section` (TraceContext.node_const) at the node"""
+        return self._intern("nodec", (section, cid))
+
     def op(self, name, *args):
         # x*1.0 and x/1.0 are exact identities in IEEE-754 (the reference multiplies and
         # divides by unit 1.0 all the time, optimize.py:284,1018,1125)
@@ -94,19 +98,22 @@ class Graph:
         return self._intern("interp", (x,), float(table_id))
 
 
-def substitute_blocks(graph, node, fn, memo):
-    """Rebuild `node` with every ('blk', s, b) leaf replaced by fn(s, b)."""
+def substitute_blocks(graph, node, fn, memo, fn_nodec=None):
+    """Rebuild `node` with every ('blk', s, b) leaf replaced by fn(s, b) (and every ('nodec', s, cid)
+    leaf by fn_nodec(s, cid) if given)."""
     got = memo.get(node.uid)
     if got is not None:
         return got
     if node.op == "blk":
         out = fn(*node.args)
+    elif node.op == "nodec":
+        out = fn_nodec(*node.args) if fn_nodec is not None else node
     elif node.op in ("const", "var"):
         out = node
     elif node.op == "interp":
-        out = graph.interp(int(node.value), substitute_blocks(graph, node.args[0], fn, memo))
+        out = graph.interp(int(node.value), substitute_blocks(graph, node.args[0], fn, memo, fn_nodec))
     else:
-        out = graph.op(node.op, *[substitute_blocks(graph, a, fn, memo) for a in node.args])
+        out = graph.op(node.op, *[substitute_blocks(graph, a, fn, memo, fn_nodec) for a in node.args])
     memo[node.uid] = out
     return out
 
@@ -125,6 +132,8 @@ def leaves(node, seen=None, out=None):
             out.add(("blk",) + n.args)
         elif n.op == "var":
             out.add(("var",) + n.args)
+        elif n.op == "nodec":
+            out.add(("nodec",) + n.args)
         else:
             stack.extend(n.args)
     return out
@@ -151,6 +160,37 @@ class TraceContext:
         self.nvars = o + self.nsec
         self.tables = []              # lookup tables met while tracing: dicts x, y, variant, ...
         self._table_ids = {}
+        self.node_consts = [[] for _ in range(self.nsec)]    # per phase: constant vectors, one value per node
+        self._node_const_ids = {}
+
+    def node_const(self, s, values):
+        """Register a per-node constant vector of phase s (prob.time[s], prob.tau[s], a user table of one
+        value per node ...); returns its id within the phase."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.shape == (self.nodes[s],)
+        key = (s, v.tobytes())
+        if key not in self._node_const_ids:
+            self.node_consts[s].append(v.copy())
+            self._node_const_ids[key] = len(self.node_consts[s]) - 1
+        return self._node_const_ids[key]
+
+    def const_vector(self, rng, values):
+        """A numpy vector aligned with the node range rng as a traced vector of per-node constants, or None
+        if rng does not consist of whole phases (the caller then expands element by element)."""
+        glo, ghi = rng
+        parts, at = {}, glo
+        for s in range(self.nsec):
+            lo, hi = self.g0[s], self.g0[s] + self.nodes[s]
+            if hi <= glo or lo >= ghi:
+                continue
+            if lo < glo or hi > ghi:
+                return None
+            parts[s] = self.graph.nodec(s, self.node_const(s, values[lo - glo:hi - glo]))
+            at = hi
+        return Sym(self, rng, parts) if parts else None
+
+    def is_time_var(self, index):
+        return index >= self.nvars - self.nsec
 
     def table_of(self, f):
         """Register a scipy.interpolate.interp1d object; returns its table id."""
@@ -278,7 +318,8 @@ class Sym:
         s = ctx.section_of(g)
         kl = g - ctx.g0[s]
         node = substitute_blocks(ctx.graph, self.parts[s],
-                                 lambda sec, b: ctx.graph.var(ctx.var_index(sec, b, kl)), {})
+                                 lambda sec, b: ctx.graph.var(ctx.var_index(sec, b, kl)), {},
+                                 lambda sec, cid: ctx.graph.const(ctx.node_consts[sec][cid][kl]))
         return Sym(ctx, None, node)
 
     def __getitem__(self, key):
@@ -313,7 +354,24 @@ class Sym:
     def _bin(self, name, other, swap=False):
         if isinstance(other, SymList):
             return NotImplemented
+        if isinstance(other, (list, tuple)) and len(other) and all(_is_number(v) for v in other):
+            other = np.asarray(other, dtype=np.float64)
         if isinstance(other, np.ndarray) and other.ndim > 0:
+            # one value per node of the same node range: a per-node constant vector (prob.time[s], prob.tau[s],
+            # a user table) -- stays node-local; anything else is expanded element by element
+            if other.ndim == 1 and self.rng is not None and len(other) == len(self) and other.dtype.kind in "fiu":
+                vec = self.ctx.const_vector(self.rng, other.astype(np.float64))
+                if vec is not None:
+                    return self._bin(name, vec, swap)
+            if other.ndim == 1 and self.rng is None and other.dtype.kind in "fiu":
+                # a traced scalar (a final time) with a table of one value per node: the table's node range is the
+                # one phase with that many nodes, or all phases
+                ctx = self.ctx
+                cands = [(ctx.g0[s], ctx.g0[s] + ctx.nodes[s]) for s in range(ctx.nsec) if ctx.nodes[s] == len(other)]
+                if len(other) == ctx.gtot and ctx.nsec > 1:
+                    cands.append((0, ctx.gtot))
+                if len(cands) == 1:
+                    return self._bin(name, ctx.const_vector(cands[0], other.astype(np.float64)), swap)
             return SymList.from_any(self)._bin(name, other, swap)
         try:
             o = _coerce(self.ctx, other)
@@ -679,18 +737,29 @@ class TraceView:
     # unless overridden below with a traced version.
     _PASS = frozenset((
         "nodes", "number_of_states", "number_of_controls", "number_of_section", "number_of_variables",
-        "number_of_param", "div", "tau", "w", "D", "time", "time_all_section", "time_init", "t0",
+        "number_of_param", "div", "D", "time_init", "t0",
         "unit_states", "unit_controls", "unit_time", "maxIterator", "iterator", "bounds",
         "knot_states_smooth", "dynamics", "cost", "running_cost", "cost_derivative", "equality",
         "inequality", "index_states", "index_controls", "index_time_final", "time_to_tau",
         "_division_states", "_division_controls", "_span_state", "_span_control", "bounds_arrays",
         "backend", "device"))
 
+    def _node_vectors(self, arrays):
+        ctx = self._ctx
+        return [ctx.const_vector((ctx.g0[s], ctx.g0[s] + ctx.nodes[s]), np.asarray(arrays[s], dtype=float))
+                for s in range(ctx.nsec)]
+
     def __getattr__(self, name):
         if name == "p":
             raise TraceError("direct access to prob.p inside a callback cannot be traced; "
                              "use prob.states()/controls()/time_final()")
         prob = self._prob
+        # per-node data of the problem: traced vectors of per-node constants, so that they combine with traced
+        # scalars (final times) as well as with state / control vectors and stay node-local
+        if name in ("tau", "w", "time"):
+            return self._node_vectors(getattr(prob, name))
+        if name == "time_all_section":
+            return self._ctx.const_vector((0, self._ctx.gtot), np.asarray(prob.time_all_section, dtype=float))
         if name in self._PASS or (name in vars(prob) and not hasattr(type(prob), name)):
             return getattr(prob, name)          # whitelisted, or an attribute the user attached
         if hasattr(prob, name):
@@ -754,6 +823,18 @@ class TraceView:
     def time_knots(self):
         # reference optimize.py:533-540 ([0] + final times; the reference assumes t0 = 0 here)
         return [0] + self.time_final_all_section()
+
+    def time_update(self):
+        """reference optimize.py:518-531 as a traced vector over all nodes: per phase (t_{s+1} - t_s) / 2 * tau_s
+        + (t_{s+1} + t_s) / 2 with t = [0] + final times -- final-time scalars times the per-node constants tau.
+        (The reference also stores the result in prob.time; a traced callback has no side effects.)"""
+        ctx = self._ctx
+        t = self.time_knots()
+        parts = {}
+        for s in range(ctx.nsec):
+            seg = (t[s + 1] - t[s]) / 2.0 * self.tau[s] + (t[s + 1] + t[s]) / 2.0
+            parts[s] = seg.parts[s]
+        return Sym(ctx, (0, ctx.gtot), parts)
 
 
 class interp1d_tracing:

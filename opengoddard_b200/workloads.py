@@ -924,3 +924,75 @@ def all_ops(api, nodes=(9, 6)):
 
 
 CONFIGS["edge_all_ops"] = (all_ops, (9, 6))
+
+
+def nonautonomous(api, nodes=(11, 8)):
+    """Edge case: explicitly time-dependent callbacks, legal in the reference because it evaluates them eagerly
+    (optimize.py:685): the dynamics read the phase's final / start time (`prob.time_final(s)`, :349-360), the
+    LGL abscissae `prob.tau[s]` (per-node constants, :786-791) and a user table with one value per node; a path
+    constraint and the running cost use `prob.time_update()` (:518-531).  On the device the final times become
+    global inputs of the node programs, whose Jacobian columns are dense in the phases that read them."""
+    class Obj:
+        pass
+
+    obj = Obj()
+    rng = np.random.default_rng(12)
+    obj.gust = [0.2 * rng.standard_normal(N) for N in nodes]
+    prob = api.Problem([0.0, 1.5, 4.0], list(nodes), [2, 2], [1, 1], 5)
+    # (a copy of the initial time grid: prob.time itself is overwritten by every time_update() call in the
+    # reference, optimize.py:526-530, so reading it in one callback and calling time_update() in another would
+    # make the result depend on the order SciPy calls them in)
+    obj.ramp = [np.array(t, dtype=float) for t in prob.time]
+    prob.set_unit_states_all_section(1, 2.0)
+    prob.set_unit_time(2.0)
+
+    def dyn(prob, obj, section):
+        x = prob.states(0, section)
+        v = prob.states(1, section)
+        u = prob.controls(0, section)
+        tf = prob.time_final(section)
+        t0 = prob.time_start(section)
+        t = (tf - t0) / 2.0 * prob.tau[section] + (tf + t0) / 2.0        # physical time at the nodes
+        d = api.Dynamics(prob, section)
+        d[0] = v + obj.gust[section] * np.sin(0.7 * t)
+        d[1] = u - 0.3 * v * t / tf + 0.1 * x * obj.ramp[section]
+        return d()
+
+    def eq(prob, obj):
+        r = api.Condition()
+        r.equal(prob.states(0, 0)[0], 0.0)
+        r.equal(prob.states(1, 0)[0], 0.5, unit=2.0)
+        r.equal(prob.states(0, 1)[-1], 3.0)
+        return r()
+
+    def ineq(prob, obj):
+        r = api.Condition()
+        r.lower_bound(prob.states_all_section(0) + 0.05 * prob.time_update(), -5.0)
+        r.upper_bound(prob.controls_all_section(0), 2.0)
+        r.lower_bound(prob.time_final(0), 0.5)
+        return r()
+
+    def running(prob, obj):
+        u = prob.controls_all_section(0)
+        return u ** 2 * (1.0 + 0.1 * prob.time_update())
+
+    def cost(prob, obj):
+        return prob.time_final(-1)
+
+    t = prob.time_all_section
+    G = api.Guess
+    prob.set_states_all_section(0, G.linear(t, 0.0, 3.0))
+    prob.set_states_all_section(1, G.cubic(t, 0.5, 0.2, 1.0, -0.1))
+    prob.set_controls_all_section(0, G.linear(t, 0.6, -0.2))
+    prob.set_controls_bounds_all_section(0, -2.5, 2.5)
+    prob.dynamics = [dyn, dyn]
+    prob.knot_states_smooth = [True]
+    prob.cost = cost
+    prob.running_cost = running
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("nonautonomous", prob, obj, None)
+
+
+CONFIGS["edge_nonautonomous"] = (nonautonomous, (11, 8))
+CONFIGS["edge_nonautonomous_big"] = (nonautonomous, (40, 33))

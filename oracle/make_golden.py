@@ -49,6 +49,7 @@ WORKLOAD_INSTANCES = {
     "ex05_goddard_knot25x2": 2,
     "ex09_polar_tsto20x2": 2,
     "ex10_lowthrust100": 1,
+    "edge_nonautonomous": 2,
 }
 
 

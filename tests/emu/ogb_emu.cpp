@@ -71,6 +71,7 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
     W.px1 = mem.data() + pl.o_px1; W.scpert = mem.data() + pl.o_scpert; W.G = pl.G;
     W.pdlt = mem.data() + pl.o_pdlt; W.pcol = reinterpret_cast<OgbCol*>(mem.data() + pl.o_pcol);
     W.cf = mem.data() + pl.o_cf; W.rterm = mem.data() + pl.o_rterm; W.costp = mem.data() + pl.o_costp; W.prdx = mem.data() + pl.o_prdx;
+    W.gpert = mem.data() + pl.o_gpert;
     std::vector<double> tilev(P.M);
     double* tile = tilev.data();
     std::vector<double> pclip(P.n), dxs(P.ndx);
@@ -87,7 +88,7 @@ int emu_eval(void* h, const double* p, const double* lb, const double* ub, doubl
             const int ncols = with_fd ? std::min(pl.group, P.n - jlo) : 0;
             for (int j = 0; j < P.n; ++j) W.sp[j] = pclip[j];
             for (int e = 0; e < P.ndx; ++e) W.sdx[e] = dxs[e];
-            for (int q = 0; q < P.gtot + 1 + ncols; ++q) ogb_job(P, W, q, jlo, lb, ub, abs_step);
+            for (int q = 0; q < ogb_njobs(P, ncols); ++q) ogb_job(P, W, q, jlo, ncols, lb, ub, abs_step);
             ogb_assemble_base(P, W, 0, 1);
             ogb_assemble_cost(P, W);
             for (int cl = 0; cl < ncols; ++cl) ogb_cost_column(P, W, cl);
@@ -126,6 +127,7 @@ int emu_eval_exact(void* h, const double* p, const double* lb, const double* ub,
     W.px1 = mem.data() + pl.o_px1; W.scpert = mem.data() + pl.o_scpert; W.G = pl.G;
     W.pdlt = mem.data() + pl.o_pdlt; W.pcol = reinterpret_cast<OgbCol*>(mem.data() + pl.o_pcol);
     W.cf = mem.data() + pl.o_cf; W.rterm = mem.data() + pl.o_rterm; W.costp = mem.data() + pl.o_costp; W.prdx = mem.data() + pl.o_prdx;
+    W.gpert = mem.data() + pl.o_gpert;
     std::vector<double> tilev(P.M), pclip(P.n), dxs(P.ndx);
     double* tile = tilev.data();
     for (int b = 0; b < B; ++b) {
@@ -136,7 +138,7 @@ int emu_eval_exact(void* h, const double* p, const double* lb, const double* ub,
             const int ncols = std::min(pl.group, P.n - jlo);
             for (int j = 0; j < P.n; ++j) W.sp[j] = pclip[j];
             for (int e = 0; e < P.ndx; ++e) W.sdx[e] = dxs[e];
-            for (int q = 0; q < P.gtot + 1 + ncols; ++q) ogb_job_exact(P, W, q, jlo);
+            for (int q = 0; q < ogb_njobs(P, ncols); ++q) ogb_job_exact(P, W, q, jlo, ncols);
             ogb_assemble_base(P, W, 0, 1);
             ogb_assemble_cost(P, W);
             for (int cl = 0; cl < ncols; ++cl) ogb_cost_column_exact(P, W, cl);

@@ -18,7 +18,8 @@ FD_VS_EXACT_RTOL = 1e-4      # the forward-difference Jacobian against the exact
 #                              exact mode removes, not a defect of either
 
 CFGS = ["cfg1_brachistochrone20", "cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40",
-        "cfg5_lowthrust128", "ex09_polar_tsto20x2", "edge_table_lookup", "edge_all_ops"]
+        "cfg5_lowthrust128", "ex09_polar_tsto20x2", "edge_table_lookup", "edge_all_ops", "edge_nonautonomous",
+        "edge_nonautonomous_big"]
 
 
 def oracle_jacobian(wo, x, lb, ub):

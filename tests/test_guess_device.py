@@ -70,8 +70,9 @@ def test_device_guess_batch_matches_the_reference_setters(api, name):
     nsec, ns, nc = prob.number_of_section, prob.number_of_states[0], prob.number_of_controls[0]
     B = 6
     rng = np.random.default_rng(5)
+    # (distinct variables: the specs are written concurrently; state ns - 1 >= 2 in these problems)
     specs = [("linear", ("state", 0), None), ("cubic", ("state", 1), None), ("constant", ("control", 0), None),
-             ("linear", ("state", ns - 1), nsec - 1), ("zeros", ("control", nc - 1), 0)]
+             ("linear", ("state", ns - 1), nsec - 1)] + ([("zeros", ("control", nc - 1), 0)] if nc > 1 else [])
     params = rng.normal(size=(B, len(specs), 4)) * 3.0
     tfinal = np.sort(rng.uniform(0.5, 3.0, size=(B, nsec)), axis=1) * prob.unit_time
     P = prob.guess_batch(specs, params, wl.obj, tfinal=tfinal).cpu().numpy()
@@ -83,7 +84,8 @@ def test_device_guess_batch_matches_the_reference_setters(api, name):
         ref.set_states_all_section(1, G.cubic(t_all, *params[b, 1]))
         ref.set_controls_all_section(0, G.constant(t_all, params[b, 2, 0]))
         ref.set_states(ns - 1, nsec - 1, G.linear(ref.time[nsec - 1], params[b, 3, 0], params[b, 3, 1]))
-        ref.set_controls(nc - 1, 0, G.zeros(ref.time[0]))
+        if nc > 1:
+            ref.set_controls(nc - 1, 0, G.zeros(ref.time[0]))
         for s in range(nsec):
             ref.set_time_final(s, tfinal[b, s])
         scale = np.abs(ref.p).max()
@@ -91,6 +93,9 @@ def test_device_guess_batch_matches_the_reference_setters(api, name):
         lin_idx = np.arange(prob.index_states(0, 0), prob.index_states(0, 0) + prob.nodes[0])
         assert np.array_equal(P[b][lin_idx], ref.p[lin_idx])           # the linear block: bit-identical
         assert np.array_equal(P[b][-nsec:], ref.p[-nsec:])
+    from opengoddard_b200 import capi
+    with pytest.raises(capi.OgbError):                                    # overlapping specs are refused
+        prob.guess_batch([("linear", ("state", 0), None), ("zeros", ("state", 0), 0)], params[:, :2], wl.obj)
 
 
 @pytest.mark.gpu

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 CFGS = ["cfg1_brachistochrone20", "cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40",
         "cfg5_lowthrust128", "ex05_goddard_knot25x2", "ex09_polar_tsto20x2", "ex10_lowthrust100",
-        "edge_table_lookup", "edge_stress_mixed", "edge_all_ops"]
+        "edge_table_lookup", "edge_stress_mixed", "edge_all_ops", "edge_nonautonomous", "edge_nonautonomous_big"]
 
 
 @pytest.fixture(scope="module")
@@ -64,7 +64,7 @@ def test_split_pipeline_full_size_on_a_side_stream(torch_cuda, api):
     P = t.from_numpy(workloads.make_batch(wl, 4096)).cuda()
     eng.set_option(9, 0)
     c0, J0 = eng.eval_fd(P)
-    eng.set_option(9, -1)                                       # auto: 3 GB of J -> split
+    eng.set_option(9, 1)                                        # the split pipeline, automatic chunk size
     side = t.cuda.Stream()
     side.wait_stream(t.cuda.current_stream())
     with t.cuda.stream(side):

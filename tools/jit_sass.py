@@ -19,7 +19,7 @@ out = "/tmp/ogbjit"
 os.makedirs(out, exist_ok=True)
 packed = 1 if "--packed" in sys.argv else 0          # which of the two kernels (dense / packed output) to look at
 src += ("\ntemplate __global__ void ogb_sweep_kernel<%d, %d>(OgbProb, OgbPlan, const double*, const double*, const double*, "
-        "const double*, double, int, double*, double*, int, int, int, int, int, unsigned long long*, unsigned long long);\n" % (nr, packed))
+        "const double*, double, int, double*, double*, int, int, int, int, int, unsigned long long*, unsigned long long, int);\n" % (nr, packed))
 open(out + "/ogb_jit.cu", "w").write(src)
 cmd = ["nvcc", "-cubin", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false", "-lineinfo",
        "-Xptxas", "-v", "-I", ROOT + "/opengoddard_b200/csrc", "-I", ROOT + "/include", "-o", out + "/k.cubin", out + "/ogb_jit.cu"]
