@@ -183,8 +183,10 @@ enum ogb_option {
                                     Results are bit-identical either way.                                         */
     OGB_OPT_SPLIT_CHUNK = 10,    /* instances per chunk of the split pipeline (0 = auto, ~192 MB of dense J)        */
     OGB_OPT_DENSE_STREAMING = 11,/* 1 (default): K2b writes its zeros with st.global.cs (evict-first)              */
-    OGB_OPT_ZERO_MODE = 12,      /* experiments on the fused kernel's zero stream (results unchanged): bit 0 = st.global.cs
-                                    stores, bit 1 = the CTA fills the item's whole region first, then scatters     */
+    OGB_OPT_ZERO_MODE = 12,      /* how the fused kernel writes its zeros (results unchanged): 0 = every warp streams the
+                                    zeros of its own column, then overwrites the non-zeros; bit 0 = with st.global.cs
+                                    (measured slower); 4 / 8 = one / two dedicated writer warps per CTA stream the
+                                    zeros of the CTA's next work item while the other warps compute                */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
                                     launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
                                     (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */

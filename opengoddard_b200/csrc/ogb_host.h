@@ -99,7 +99,7 @@ static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, si
     pl->o_tiles = pl->o_tail = o;                          // (no column staging: J is written directly)
     pl->tile_stride = pl->tail_stride = 0;
     pl->o_end = o;
-    pl->smem_bytes = o * 8 + 32;   // + 2 mbarriers + the next-item slot
+    pl->smem_bytes = o * 8 + 32;   // + 2 mbarriers + two next-item slots
     pl->TC = warps;
     pl->threads = warps * 32;
     pl->nbuf = 2;

@@ -124,7 +124,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     W.G = pl.G;
     OgbSlot* slots = reinterpret_cast<OgbSlot*>(smem + pl.o_slot);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + pl.o_end);     // [2]
-    volatile long* s_next = reinterpret_cast<volatile long*>(smem + pl.o_end + 2);   // next work item
+    volatile long* s_next = reinterpret_cast<volatile long*>(smem + pl.o_end + 2);   // next work item [2] (by item parity)
 
     // ---- once per CTA: problem descriptors and tapes into shared memory
     {
@@ -152,6 +152,14 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     __syncthreads();
 
     const int n = P.n, M = P.M, ndx = P.ndx;
+    // Writer warps (OGB_OPT_ZERO_MODE bits 2-3; dense FD output only): the last one or two warps of the CTA do
+    // nothing but stream the zeros of the CTA's NEXT work item -- its whole region, linearly, 512 bytes per
+    // instruction -- while the other (compute) warps run the tapes, assemble c and scatter the non-zeros of the
+    // current item, so the SM's store path stays busy through the latency-bound phases.  One full-CTA barrier
+    // per item hands over (the next item's index one way, "its zeros are written" the other way); every other
+    // barrier of the item loop involves the compute warps only.
+    const int nwr = (PACKED_OUT == 0 && with_fd == 1 && (zero_mode & 12) && (nthr >> 5) >= 4) ? ((zero_mode & 8) ? 2 : 1) : 0;
+    const int cwarps = (nthr >> 5) - nwr, cnthr = cwarps * 32;        // compute warps / threads
     const int nchunk = with_fd ? pl.split : 1;
     const long nitems = (long)B * nchunk;
     const bool fused_dx = DX == nullptr;            // D.X by in-kernel DMMA instead of K1's scratch
@@ -173,7 +181,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             if (bp) bulk_g2s(sp + hp, gp + hp, (uint32_t)bp * 8u, mbar + st);
             if (bd) bulk_g2s(sdx + hd, gdx + hd, (uint32_t)bd * 8u, mbar + st);
         }
-        if (tid == (nthr > 32 ? 32 : 0)) {      // (a one-warp CTA: thread 0 does both)
+        if (tid == (cnthr > 32 ? 32 : 0)) {      // (a one-warp CTA: thread 0 does both)
             if (hp) sp[0] = gp[0];
             for (int e = hp + bp; e < n; ++e) sp[e] = gp[e];
             if (!fused_dx) {
@@ -189,8 +197,42 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     // its index) so all CTAs finish within one item of each other.  The ticket for item i+1 is
     // requested at the top of item i and read after the tape phase (its latency is off the critical
     // path); the inputs of item i+1 are then prefetched while item i assembles and streams out.
+    auto csync = [&]() {
+        if (nwr) asm volatile("bar.sync 1, %0;" ::"r"(cnthr) : "memory");
+        else __syncthreads();
+    };
+    // zeros of one work item's region J[b, jlo .. jlo + ncols, :] by `nw` warps (this thread: lane of warp `w`)
+    auto zero_item = [&](long item, int w, int nw) {
+        const long zb = item / nchunk;
+        const int zch = (int)(item - zb * nchunk);
+        const int zlo = zch * pl.group, zn = min(pl.group, n - zlo);
+        double* reg = J + (size_t)zb * n * (size_t)M + (size_t)zlo * (size_t)M;
+        const size_t len = (size_t)zn * (size_t)M;
+        const size_t hj = (reinterpret_cast<uintptr_t>(reg) >> 3) & 1;
+        const size_t nv = (len - hj) >> 1;                       // 16-byte pieces
+        double2* v = reinterpret_cast<double2*>(reg + hj);
+        const double2 z2 = make_double2(0.0, 0.0);
+        const size_t step = (size_t)nw * 32;
+        size_t i = (size_t)w * 32 + lane;
+        for (; i + 3 * step < nv; i += 4 * step) { v[i] = z2; v[i + step] = z2; v[i + 2 * step] = z2; v[i + 3 * step] = z2; }
+        for (; i < nv; i += step) v[i] = z2;
+        if (w == 0 && lane == 0 && hj) reg[0] = 0.0;
+        if (w == 0 && lane == 1 && ((len - hj) & 1)) reg[len - 1] = 0.0;
+    };
+    if (nwr && (long)blockIdx.x < nitems) zero_item(blockIdx.x, warp, cwarps + nwr);   // the first item: all warps
+    if (nwr && warp >= cwarps) {
+        // ---- writer warps: zero the next item while the compute warps work on the current one
+        unsigned wit = 0;
+        for (long item = blockIdx.x; item < nitems; ++wit) {
+            __syncthreads();                                     // hand-over: the compute warps published the next item
+            const long nx = s_next[wit & 1u];
+            if (nx < nitems) zero_item(nx, warp - cwarps, nwr);
+            item = nx;
+        }
+        return;
+    }
     if ((long)blockIdx.x < nitems) stage_inputs(blockIdx.x, 0);
-    __syncthreads();                 // the odd head / tail doubles of the first item are in place
+    csync();                 // the odd head / tail doubles of the first item are in place
     unsigned it = 0;
     for (long item = blockIdx.x; item < nitems; ++it) {
         const long b = item / nchunk;
@@ -212,12 +254,12 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         }
         mbar_wait(mbar + st, (it >> 1) & 1u);      // TMA bytes are visible to every thread that waited
         if (with_fd) {               // _check_clip_x (scipy/optimize/_slsqp_py.py:355)
-            for (int j = tid; j < n; j += nthr) {
+            for (int j = tid; j < n; j += cnthr) {
                 const double x = W.sp[j], lo = lb[j], hi = ub[j];
                 W.sp[j] = x < lo ? lo : (x > hi ? hi : x);
             }
         }
-        __syncthreads();
+        csync();
 
         // ---- phase 2a: D.X of this instance on the FP64 tensor cores (K1 fused in): per phase
         //      OUT[a, i] = sum_l X[a, l] * D[i, l] as m8n8k4 DMMAs, A = the (clipped,
@@ -232,7 +274,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 const int N = S.N, Kp = (N + 3) & ~3;
                 const int mt = (S.ns + 7) >> 3, nt = (N + 7) >> 3;
                 const double* __restrict__ Dm = P.D + S.doff;
-                for (int u = warp - unit0 % nwarps; u < mt * nt; u += nwarps) {
+                for (int u = warp - unit0 % cwarps; u < mt * nt; u += cwarps) {
                     if (u < 0) continue;
                     const int a = (u / nt) * 8 + qr, i0 = (u % nt) * 8;
                     const bool av_ok = a < S.ns;
@@ -259,36 +301,36 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
 
         // ---- phase 2: tapes -- base nodes, scalar program, one job per Jacobian column
         if (PACKED_OUT == 2) {
-            for (int q = tid; q < ogb_njobs(P, ncols); q += nthr) ogb_job_exact(P, W, q, jlo, ncols);
+            for (int q = tid; q < ogb_njobs(P, ncols); q += cnthr) ogb_job_exact(P, W, q, jlo, ncols);
         } else if (with_fd != 5)        // (probe 5: no tapes, no assembly -- the zero stream alone)
-        for (int q = tid; q < ogb_njobs(P, ncols); q += nthr) ogb_job(P, W, q, jlo, ncols, lb, ub, abs_step);
-        if (tid == 0) *s_next = claimed;
-        __syncthreads();
-        const long next_item = *s_next;
+        for (int q = tid; q < ogb_njobs(P, ncols); q += cnthr) ogb_job(P, W, q, jlo, ncols, lb, ub, abs_step);
+        if (tid == 0) s_next[it & 1u] = claimed;
+        __syncthreads();             // (with writer warps: the one barrier of the item they take part in)
+        const long next_item = s_next[it & 1u];
         if (next_item < nitems) stage_inputs(next_item, st ^ 1);      // prefetch one item ahead
 
         // ---- phase 3: c at the base point and the perturbed cost of every column.  Without a
         //      running cost neither depends on the other, so one barrier covers both.
-        if (with_fd != 5) ogb_assemble_base(P, W, tid, nthr);
+        if (with_fd != 5) ogb_assemble_base(P, W, tid, cnthr);
         if (!P.has_running && with_fd != 5) {
             if (tid == 0) ogb_assemble_cost(P, W);
-            for (int cl = tid; cl < ncols; cl += nthr) {
+            for (int cl = tid; cl < ncols; cl += cnthr) {
                 if (PACKED_OUT == 2) ogb_cost_column_exact(P, W, cl); else ogb_cost_column(P, W, cl);
             }
         }
-        __syncthreads();
+        csync();
         if (P.has_running) {
             if (tid == 0) ogb_assemble_cost(P, W);
-            __syncthreads();
-            for (int cl = tid; cl < ncols; cl += nthr) {
+            csync();
+            for (int cl = tid; cl < ncols; cl += cnthr) {
                 if (PACKED_OUT == 2) ogb_cost_column_exact(P, W, cl); else ogb_cost_column(P, W, cl);
             }
-            __syncthreads();
+            csync();
         }
         if (ch == 0)
-            for (int r = tid; r < M; r += nthr) c[b * M + r] = W.sc[r];
+            for (int r = tid; r < M; r += cnthr) c[b * M + r] = W.sc[r];
 
-        // ---- phase 4: Jacobian columns, one warp per column (columns warp, warp + nwarps, ...),
+        // ---- phase 4: Jacobian columns, one warp per column (columns warp, warp + cwarps, ...),
         //      no block barrier and no staging: the warp streams the column's zeros to HBM with
         //      16-byte stores, then (ordered by __syncwarp) overwrites the few rows that can be
         //      non-zero.  The overwrites hit sectors still resident in L2, so DRAM sees each
@@ -298,32 +340,18 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         //      (shared memory through constant offsets, D^T through the read-only path), the zero
         //      stream is issued while those loads fly, and the column pointer is carried from
         //      iteration to iteration instead of being rebuilt from (instance, column) per store.
-        // zero_mode (experiments, OGB_OPT_ZERO_MODE): bit 0 = streaming (st.global.cs) zero stores; bit 1 = the
-        // CTA fills the item's whole region [jlo, jlo + ncols) x M linearly first (aligned 16-byte stores, one
-        // block barrier), the warps then only scatter the non-zeros
-        const bool zero_cs = (zero_mode & 1) != 0, zero_cta = (zero_mode & 2) != 0 && PACKED_OUT == 0 && with_fd == 1;
-        if (zero_cta) {
-            double* reg = J + (size_t)b * n * (size_t)M + (size_t)jlo * (size_t)M;
-            const size_t len = (size_t)ncols * (size_t)M;
-            const size_t hj = (reinterpret_cast<uintptr_t>(reg) >> 3) & 1;
-            const size_t nv = (len - hj) >> 1;
-            double2* v = reinterpret_cast<double2*>(reg + hj);
-            const double2 z2 = make_double2(0.0, 0.0);
-            if (zero_cs) { for (size_t i = tid; i < nv; i += nthr) __stcs(v + i, z2); }
-            else { for (size_t i = tid; i < nv; i += nthr) v[i] = z2; }
-            if (tid == 0 && hj) reg[0] = 0.0;
-            if (tid == 32 % nthr && ((len - hj) & 1)) reg[len - 1] = 0.0;
-            __syncthreads();
-        }
+        // zero_mode (experiments, OGB_OPT_ZERO_MODE): bit 0 = streaming (st.global.cs) zero stores (measured slower);
+        // bits 2-3 = dedicated writer warps (see below)
+        const bool zero_cs = (zero_mode & 1) != 0;
         auto columns = [&](auto packed_tag) {
             constexpr bool PACKED = decltype(packed_tag)::value;
             constexpr int NRA = NR > 0 ? NR : 1;
             // dense: J[b, j, :] of the first column of this warp; packed: the instance's values [nnz]
             double* gdst = PACKED ? J + (size_t)b * (size_t)P.nnz
                                   : J + (size_t)b * n * (size_t)M + (size_t)(jlo + warp) * (size_t)M;
-            const size_t gstep = PACKED ? 0 : (size_t)nwarps * (size_t)M;
+            const size_t gstep = PACKED ? 0 : (size_t)cwarps * (size_t)M;
             const int* pm = PACKED ? P.pmap + (size_t)(jlo + warp) * (size_t)M : nullptr;   // row -> packed entry
-            const size_t pmstep = (size_t)nwarps * (size_t)M;
+            const size_t pmstep = (size_t)cwarps * (size_t)M;
             int cur_key = -1, slot_sec = -1;
             double r_sdx[NRA], r_cf[NRA], r_sc[NRA];
             OgbSlot si = {0, 0, 0, 0};               // where this lane's output slot lands (per phase)
@@ -336,7 +364,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             const double* const s_coef = smem + pl.o_coef;
             const int4* const s_pcol = reinterpret_cast<const int4*>(smem + pl.o_pcol);
             const double* const s_sdx = W.sdx;       // (the input stage alternates between items)
-            for (int cc = warp; cc < ncols; cc += nwarps, gdst += gstep, pm += (PACKED ? pmstep : 0)) {
+            for (int cc = warp; cc < ncols; cc += cwarps, gdst += gstep, pm += (PACKED ? pmstep : 0)) {
                 asm volatile("" : "+l"(gdst));       // keep the column pointer in registers ...
                 __builtin_assume(__isGlobal(gdst));  // ... and its stores in the global space (STG, not ST)
                 // (A) operands
@@ -372,7 +400,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 // (B) zeros: 16-byte aligned body, an odd first / last double on its own
                 //     (with_fd == 2: structure probe -- only the overwrites below land, on a
                 //      sentinel-filled J; see ogb_jac_pattern.  3 / 4 / 5: timing probes)
-                if (!PACKED && with_fd != 2 && with_fd != 4 && !zero_cta) {
+                if (!PACKED && with_fd != 2 && with_fd != 4 && !nwr) {
                     const unsigned hj = (unsigned)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
                     const unsigned nbytes = ((unsigned)(M - hj) & ~1u) * 8u;
                     char* g = reinterpret_cast<char*>(gdst + hj) + lane * 16;
@@ -474,12 +502,12 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         if (PACKED_OUT == 2) {
             // exact mode: one warp per column, every structural non-zero straight into the packed values
             double* vb = J + (size_t)b * (size_t)P.nnz;
-            for (int cc = warp; cc < ncols; cc += nwarps)
+            for (int cc = warp; cc < ncols; cc += cwarps)
                 ogb_scatter_column_exact(P, W, jlo + cc, cc, OgbColPacked{vb, P.pmap + (size_t)(jlo + cc) * (size_t)M}, lane, 32);
         } else {
             columns(OgbBool<PACKED_OUT != 0>{});
         }
-        __syncthreads();             // all warps are done reading this item's staging
+        csync();             // all warps are done reading this item's staging
         item = next_item;
     }
 }

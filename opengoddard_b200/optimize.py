@@ -516,7 +516,10 @@ class Problem:
             fun, cons, jac = self._host_callables(obj)
         ftol = options.setdefault("ftol", 1e-6)
         maxiter = options.setdefault("maxiter", 25)
-        while self.iterator < self.maxIterator:
+        # $OGB200_MAX_OUTER caps the outer restarts (test runs of the shipped scripts, which ask for up to 90)
+        cap = int(os.environ.get("OGB200_MAX_OUTER", "0") or 0)
+        first = self.iterator
+        while self.iterator < self.maxIterator and (cap <= 0 or self.iterator - first < cap):
             print("---- iteration : {0} ----".format(self.iterator + 1))
             opt = optimize.minimize(fun, self.p, args=(self, obj), bounds=self.bounds,
                                     constraints=cons, jac=jac, method="SLSQP",

@@ -25,17 +25,22 @@ if ROOT not in sys.path:
 from oracle import ref_loader  # noqa: E402
 
 EXDIR = os.path.join(ref_loader.REFERENCE_ROOT, "examples")
+# where the scripts can be RUN (they write figures / CSV files next to themselves): the copy that sits beside the
+# pip-installed reference under baseline/_ref (git-ignored, travels to the GPU box), else the reference tree
+_RUNDIR = os.path.join(ROOT, "baseline", "_ref", "examples")
+RUNDIR = _RUNDIR if os.path.isdir(_RUNDIR) else EXDIR
 GOLD = os.path.join(ROOT, "tests", "golden")
 TAGS = ("01", "02", "03", "04", "05", "06", "07", "08", "09", "10", "11")
 
 
-def run_script(tag, intercept=True, env_backend=None):
+def run_script(tag, intercept=True, env_backend=None, exdir=None):
     """exec() one shipped example with `from OpenGoddard.optimize import ...` resolving to the facade.
     intercept: Problem.solve only records (prob, obj, options).  Returns (box, globals, stdout)."""
     import OpenGoddard.optimize as api
     ref_loader.install_matplotlib_stub()
     ref_loader.install_scipy_shims()
-    script = [f for f in sorted(os.listdir(EXDIR)) if f.startswith(tag) and f.endswith(".py")][0]
+    exdir = exdir or EXDIR
+    script = [f for f in sorted(os.listdir(exdir)) if f.startswith(tag) and f.endswith(".py")][0]
     box = {}
     real_solve = api.Problem.solve
 
@@ -43,7 +48,7 @@ def run_script(tag, intercept=True, env_backend=None):
         box["prob"], box["obj"], box["options"] = self, obj, options
 
     cwd = os.getcwd()
-    os.chdir(EXDIR)
+    os.chdir(exdir)
     if intercept:
         api.Problem.solve = fake_solve
     old = os.environ.get("OGB200_BACKEND")

@@ -1,6 +1,6 @@
 """Round-2 probe: how the fused sweep kernel should write its zeros (OGB_OPT_ZERO_MODE): 0 = per column by
-the warp that owns it (round 1), 1 = the same with st.global.cs, 2 = the CTA fills the item's region linearly
-first (one barrier), 3 = 2 with st.global.cs.  K2 alone (ogb_sweep), CUDA events, L2 flushed.
+the warp that owns it (round 1), 1 = the same with st.global.cs, 4 / 8 = one / two dedicated writer warps per CTA
+zero the CTA's next work item while the other warps compute.  K2 alone (ogb_sweep), CUDA events, L2 flushed.
     python tools/zero_mode_probe.py [workload] [batch]"""
 import os
 import sys
@@ -22,10 +22,15 @@ J = torch.empty((B, n, M), dtype=torch.float64, device="cuda")
 DX = eng.dx_gemm(P, clip=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ref = None
-for threads in (256, 128):
-    eng.set_option(1, threads)
-    for mode in (0, 1, 2, 3):
+for threads in (256, 384, 128, 192, 320):
+    try:
+        eng.set_option(1, threads)
+    except Exception as ex:
+        print("threads", threads, "not possible:", str(ex)[:80])
+        continue
+    for mode in (0, 4, 8):
         eng.set_option(12, mode)
+        J.fill_(float("nan"))
         for _ in range(2):
             eng.sweep_fd(P, DX, c, J)
         best = 1e9
