@@ -79,11 +79,11 @@ def test_device_guess_batch_matches_the_reference_setters(api, name):
     G = og_numpy.Guess
     for b in range(B):
         ref.p = np.array(prob.p, dtype=float)
-        t_all = ref.time_all_section
+        t_all = prob.time_all_section        # (the facade's LGL nodes: the library's, ulps from SciPy's)
         ref.set_states_all_section(0, G.linear(t_all, params[b, 0, 0], params[b, 0, 1]))
         ref.set_states_all_section(1, G.cubic(t_all, *params[b, 1]))
         ref.set_controls_all_section(0, G.constant(t_all, params[b, 2, 0]))
-        ref.set_states(ns - 1, nsec - 1, G.linear(ref.time[nsec - 1], params[b, 3, 0], params[b, 3, 1]))
+        ref.set_states(ns - 1, nsec - 1, G.linear(prob.time[nsec - 1], params[b, 3, 0], params[b, 3, 1]))
         if nc > 1:
             ref.set_controls(nc - 1, 0, G.zeros(ref.time[0]))
         for s in range(nsec):
