@@ -671,7 +671,7 @@ def main():
     e2e_value, st = time_mode("dense", hJ, e2e_steps)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st.h2d_bytes),
            "d2h_bytes_per_step": int(st.d2h_bytes), "steps": e2e_steps,
-           "api": "ogb_host_eval_fd(mode=OGB_HOST_J_DENSE): pinned host p -> H2D -> K1 -> K2 -> K3 pack -> D2H of c "
+           "api": "ogb_host_eval_fd(mode=OGB_HOST_J_DENSE): pinned host p -> H2D -> K1 -> K2a (packed sweep) -> D2H of c "
                   "and the packed non-zeros -> %d host threads rewrite the whole dense J (zeros included) in "
                   "pageable host memory; %d chunks of %d instances; host wall clock" % (st.threads, st.nchunks, st.chunk),
            "nnz_per_instance": int(st.nnz), "host_threads": int(st.threads)}
