@@ -187,8 +187,8 @@ enum ogb_option {
                                     zeros of its own column, then overwrites the non-zeros; bit 0 = with st.global.cs
                                     (measured slower); 4 / 8 = one / two dedicated writer warps per CTA stream the
                                     zeros of the CTA's next work item while the other warps compute                */
-    OGB_OPT_GEMM_UNIT = 13,      /* K1 work unit: 0 (default) = automatic, 2 = (8-row tile, 16 output nodes) units -- more,
-                                    shorter units when the batch is too small to fill the warp slots --, 8 = whole rows */
+    OGB_OPT_GEMM_UNIT = 13,      /* K1 work unit: 0 / 8 (default) = an 8-row tile computes whole rows of D.X; 2 = (8-row tile,
+                                    16 output nodes) units (experiment: more warps in flight, measured slower)       */
     OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
                                     launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
                                     (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */

@@ -925,6 +925,29 @@ OGB_HD void ogb_cost_column_exact(const OgbProb& P, const OgbWork& W, int cl) {
     W.costp[cl] = g;
 }
 
+// knot rows of column j: +1 on the previous phase's last node, -u_post / u_prev on the next phase's first
+template <class Out>
+OGB_HD void ogb_scatter_knots_exact(const OgbProb& P, int j, const Out& col, int lane, int nlanes) {
+    for (int t = lane; t < P.nknot; t += nlanes) {
+        const OgbKnot K = P.knots[t];
+        if (K.var_prev == j) col.put(K.row, 1.0);
+        else if (K.var_post == j) col.put(K.row, -(K.u_post / K.u_prev));
+    }
+}
+// scalar-program rows of a picked variable and the cost row
+template <class Out>
+OGB_HD void ogb_scatter_scalar_cost_exact(const OgbProb& P, const OgbWork& W, const OgbCol& cd, int cl, const Out& col,
+                                          int lane, int nlanes) {
+    if (cd.pick >= 0) {
+        for (int slot = lane; slot < P.sc_nouts; slot += nlanes) {
+            const ogb_out o = P.outs[P.sc_out_off + slot];
+            if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR)
+                col.put(o.row, W.scpert[slot * P.npick + cd.pick]);
+        }
+    }
+    if (lane == 0 && ogb_col_moves_cost(P, cd)) col.put(P.M - 1, W.costp[cl]);
+}
+
 template <class Out>
 OGB_HD void ogb_scatter_column_exact(const OgbProb& P, const OgbWork& W, int j, int cl, const Out& col,
                                      int lane, int nlanes) {
@@ -950,11 +973,7 @@ OGB_HD void ogb_scatter_column_exact(const OgbProb& P, const OgbWork& W, int j, 
                     col.put(o.row + (g - o.glo), t);
             }
         }
-        for (int t = lane; t < P.nknot; t += nlanes) {
-            const OgbKnot K = P.knots[t];
-            if (K.var_prev == j) col.put(K.row, 1.0);
-            else if (K.var_post == j) col.put(K.row, -(K.u_post / K.u_prev));
-        }
+        ogb_scatter_knots_exact(P, j, col, lane, nlanes);
     } else {
         const int sec = cd.blk;
         const int slo = P.any_global ? 0 : sec, shi = P.any_global ? P.nsec : (sec + 2 < P.nsec ? sec + 2 : P.nsec);
@@ -984,12 +1003,5 @@ OGB_HD void ogb_scatter_column_exact(const OgbProb& P, const OgbWork& W, int j, 
             }
         }
     }
-    if (cd.pick >= 0) {
-        for (int slot = lane; slot < P.sc_nouts; slot += nlanes) {
-            const ogb_out o = P.outs[P.sc_out_off + slot];
-            if (o.kind == OGB_OUT_EQ_SCALAR || o.kind == OGB_OUT_INEQ_SCALAR)
-                col.put(o.row, W.scpert[slot * P.npick + cd.pick]);
-        }
-    }
-    if (lane == 0 && ogb_col_moves_cost(P, cd)) col.put(P.M - 1, W.costp[cl]);
+    ogb_scatter_scalar_cost_exact(P, W, cd, cl, col, lane, nlanes);
 }

@@ -500,10 +500,51 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             }
         };
         if (PACKED_OUT == 2) {
-            // exact mode: one warp per column, every structural non-zero straight into the packed values
+            // exact mode: one warp per column, every structural non-zero straight into the packed values.
+            // Fast path (like the FD one): the D-block of a state column is one contiguous run of packed entries
+            // holding a column of D, lane t owns output slot t of the node program.
             double* vb = J + (size_t)b * (size_t)P.nnz;
-            for (int cc = warp; cc < ncols; cc += cwarps)
-                ogb_scatter_column_exact(P, W, jlo + cc, cc, OgbColPacked{vb, P.pmap + (size_t)(jlo + cc) * (size_t)M}, lane, 32);
+            const double* const s_pert = smem + pl.o_pert;
+            const double* const s_coef = smem + pl.o_coef;
+            const int4* const s_pcol = reinterpret_cast<const int4*>(smem + pl.o_pcol);
+            int slot_sec = -1;
+            OgbSlot si = {0, 0, 0, 0};
+            for (int cc = warp; cc < ncols; cc += cwarps) {
+                const int j = jlo + cc;
+                const int* pm = P.pmap + (size_t)j * (size_t)M;
+                const int4 cdv = s_pcol[cc];
+                const OgbCol cd = {cdv.x, cdv.y, cdv.z, cdv.w};
+                const OgbColPacked col{vb, pm};
+                if (!(fast && cd.sec >= 0)) { ogb_scatter_column_exact(P, W, j, cc, col, lane, 32); continue; }
+                const OgbSec& S = ogb_sec(P, cd.sec);
+                const int N = S.N, k = cd.k, a = cd.blk < S.ns ? cd.blk : -1;
+                if (cd.sec != slot_sec) {
+                    slot_sec = cd.sec;
+                    si = lane < S.nouts ? slots[S.out_off + lane] : OgbSlot{0, 0, 0, 0};
+                }
+                const double* __restrict__ Dt = P.Dt + S.doff + k * N;
+                double dkk = 0.0;
+                if (a >= 0) {
+                    const int pos_blk = __ldg(pm + S.rdef + a * N);
+                    dkk = __ldg(Dt + k);
+                    for (int i = lane; i < N; i += 32)
+                        if (i != k) vb[pos_blk + i] = __ldg(Dt + i);
+                }
+                const double coef = s_coef[3 * cd.sec];
+                if (k >= si.klo && k < si.khi) {
+                    const double t = s_pert[lane * W.G + cc];
+                    vb[__ldg(pm + si.rbase + k)] = si.isdyn ? ((lane == a ? dkk : 0.0) - coef * t) : t;
+                }
+                for (int t2 = lane + 32; t2 < S.nouts; t2 += 32) {
+                    const OgbSlot s2 = slots[S.out_off + t2];
+                    if (k >= s2.klo && k < s2.khi) {
+                        const double t = s_pert[t2 * W.G + cc];
+                        vb[__ldg(pm + s2.rbase + k)] = s2.isdyn ? ((t2 == a ? dkk : 0.0) - coef * t) : t;
+                    }
+                }
+                if (P.nknot && (k == 0 || k == N - 1)) ogb_scatter_knots_exact(P, j, col, lane, 32);
+                if (cd.pick >= 0 || P.has_running) ogb_scatter_scalar_cost_exact(P, W, cd, cc, col, lane, 32);
+            }
         } else {
             columns(OgbBool<PACKED_OUT != 0>{});
         }
