@@ -189,9 +189,10 @@ enum ogb_option {
                                     zeros of the CTA's next work item while the other warps compute                */
     OGB_OPT_GEMM_UNIT = 13,      /* K1 work unit: 0 / 8 (default) = an 8-row tile computes whole rows of D.X; 2 = (8-row tile,
                                     16 output nodes) units (experiment: more warps in flight, measured slower)       */
-    OGB_OPT_FUSED_DX = 4         /* 0 (default): K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two
-                                    launches); 1: the sweep kernel computes D.X itself with in-kernel DMMAs
-                                    (one launch; bit-identical, measured ~8 % slower at Goddard-50 x 4096)   */
+    OGB_OPT_FUSED_DX = 4         /* 0: K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two launches); 1: the sweep
+                                    kernel computes D.X itself with in-kernel DMMAs (one launch; bit-identical);
+                                    -1 (default): automatic -- one launch for batches of at most half a wave of CTAs
+                                    (23-31 % faster at B <= 128), two launches above (8-27 % faster from B = 512)    */
 };
 int ogb_problem_set_option(void* prob, int key, int value);
 

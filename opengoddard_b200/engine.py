@@ -49,7 +49,7 @@ class DeviceProblem:
         self.ub = torch.as_tensor(np.asarray(ub, dtype=np.float64), device=self.device)
         self._work = None
         self._one = None
-        self.fused_dx = False                     # ogb_eval / ogb_eval_fd = K1 + K2 (option 4 fuses them)
+        self.fused_dx = -1                        # option 4: -1 automatic (one launch for small batches), 0 K1 + K2, 1 fused
         mode = os.environ.get("OGB200_JIT", "")
         self.jit_error = None
         if mode != "0" and (jit or mode == "require"):
@@ -85,7 +85,7 @@ class DeviceProblem:
         11 streaming zero stores in K2b."""
         self._rc(self.b.lib.ogb_problem_set_option(self.h, int(key), int(value)), "ogb_problem_set_option")
         if int(key) == 4:
-            self.fused_dx = bool(value)
+            self.fused_dx = int(value)
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream

