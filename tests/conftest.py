@@ -16,3 +16,16 @@ def pytest_configure(config):
 def api():
     import OpenGoddard.optimize as mod
     return mod
+
+
+def pytest_terminal_summary(terminalreporter):
+    """make the zero-pattern "dust" exceptions of the Jacobian comparisons visible -- entries that are 0
+    on one side and a 1-ulp forward difference (<= 1e-7 of the row maximum) on the other (libm rounding)."""
+    from tests import helpers
+    if not helpers.DUST_LOG:
+        return
+    total = sum(n for _, n, _ in helpers.DUST_LOG)
+    worst = sorted(helpers.DUST_LOG, key=lambda t: -t[1])[:5]
+    terminalreporter.write_line("J zero-pattern dust: %d entries in %d comparisons (%d Jacobian entries); largest: %s" % (
+        total, len(helpers.DUST_LOG), sum(sz for _, _, sz in helpers.DUST_LOG),
+        ", ".join("%s=%d" % (lab.split("::")[-1], n) for lab, n, _ in worst if n) or "none"))

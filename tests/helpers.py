@@ -42,12 +42,15 @@ def assert_c_close(c, c_ref, J_ref=None, x=None):
         np.abs(c - c_ref) / np.maximum(scale, 1e-300)).max()
 
 
+DUST_LOG = []          # (label, dust-level zero-pattern differences, entries compared): printed in pytest's terminal summary
+
+
 J_DUST = 1e-7          # zero-pattern exceptions: a forward difference of two values that differ by an
 #                        ulp or not at all (|entry| <= J_DUST * rowmax) may be 0 on one side only, because
 #                        CUDA's and glibc's exp/sin/cos round differently in the last place
 
 
-def assert_J_close(J, J_ref, dust=None):
+def assert_J_close(J, J_ref, dust=None, label=None):
     """J, J_ref: (..., M, n).  Row-scaled tolerance + identical zero pattern (up to FD dust:
     J_DUST * rowmax unless `dust` widens it, never beyond the value tolerance J_RTOL)."""
     dust = J_DUST if dust is None else min(float(dust), J_RTOL)
@@ -59,6 +62,10 @@ def assert_J_close(J, J_ref, dust=None):
     assert not bad.any(), "Jacobian mismatch: max row-scaled err %g" % (
         err / np.maximum(rowmax, 1e-300)).max()
     mism = (J == 0) != (J_ref == 0)
+    if label is None:
+        import os
+        label = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    DUST_LOG.append((label, int(mism.sum()), int(J.size)))
     if mism.any():
         big = np.maximum(np.abs(J), np.abs(J_ref)) > dust * rowmax
         assert not (mism & big).any(), "Jacobian zero pattern differs in %d entries (largest %g of rowmax)" % (
