@@ -9,8 +9,10 @@ callbacks once (trace.py), lowers them to device tapes (tape.py) and hands SciPy
 SLSQP `fun` / `jac` callables that resolve to the sm_100a kernels of libogb200.so
 (engine.py).  New, batched entry points: `Problem.compile`, `Problem.evaluate_batch`.
 
-Backends: "cuda" (default; raises if the library or a GPU is missing -- there is no
-silent fallback) and "host", an explicit opt-in (``prob.backend = "host"`` or
+Backends: "cuda" (default; raises if the library or a GPU is missing or a callback cannot be
+traced -- there is no silent fallback), "auto" (explicit opt-in: like "cuda", but a problem whose
+callbacks the tracer refuses is solved on the host with a RuntimeWarning naming the reason) and "host",
+an explicit opt-in (``prob.backend = "host"`` or
 ``OGB200_BACKEND=host``) that evaluates the callbacks eagerly in numpy exactly like
 the reference does; it exists for BASELINE.json's configs[0] (a single CPU instance,
 "plumbing, no GPU") and is never used by the batched hot-path API.
@@ -335,8 +337,8 @@ class Problem:
     # ------------------------------------------------------------------ B200 engine
     def _backend_name(self):
         name = self.backend or os.environ.get("OGB200_BACKEND", "cuda")
-        if name not in ("cuda", "host"):
-            raise ValueError("backend must be 'cuda' or 'host', not %r" % (name,))
+        if name not in ("cuda", "host", "auto"):
+            raise ValueError("backend must be 'cuda', 'host' or 'auto', not %r" % (name,))
         return name
 
     def _check_callbacks(self):
@@ -510,7 +512,22 @@ class Problem:
     def solve(self, obj, display_func=_dummy_func, **options):
         """solve NLP with SciPy SLSQP; ftol (default 1e-6), maxiter (default 25)"""
         self._check_callbacks()
-        if self._backend_name() == "cuda":
+        backend = self._backend_name()
+        if backend == "auto":
+            # explicit, per-problem opt-in: callbacks the tracer cannot compile for the device (cross-node reads
+            # inside dynamics, data-dependent python, ...) are evaluated eagerly in numpy like the reference does,
+            # with a warning that says so.  A missing library or GPU still raises: this is not a silent CPU path.
+            from . import trace
+            try:
+                fun, cons, jac = self._device_callables(obj)
+            except trace.TraceError as ex:
+                import warnings
+                warnings.warn("OpenGoddard-B200: this problem's callbacks cannot be compiled for the device (%s); "
+                              "backend='auto' evaluates them on the host (numpy, reference semantics) instead" % ex,
+                              RuntimeWarning, stacklevel=2)
+                self.fallback_reason = str(ex)
+                fun, cons, jac = self._host_callables(obj)
+        elif backend == "cuda":
             fun, cons, jac = self._device_callables(obj)
         else:
             fun, cons, jac = self._host_callables(obj)

@@ -332,3 +332,33 @@ def test_non_local_dynamics_are_refused_with_a_clear_message(api):
         with pytest.raises((trace.TraceError, ValueError)) as ei:
             tape.build_ir(prob, obj)
         assert "phase" in str(ei.value) or "node" in str(ei.value) or "broadcast" in str(ei.value)
+
+
+def test_backend_auto_falls_back_per_problem_with_a_warning(api, monkeypatch):
+    """an explicit, logged per-problem fallback instead of a hard TraceError.  backend="auto"
+    must be asked for; the tracer's refusal is reported in a RuntimeWarning and kept in prob.fallback_reason;
+    the solve then runs on the host like the reference (here: a brachistochrone whose dynamics read a picked
+    state, which the device path refuses)."""
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    prob, obj = wl.prob, wl.obj
+    base = prob.dynamics[0]
+
+    def dyn(p, o, s):
+        d = base(p, o, s)
+        x = p.states(0, s)
+        if isinstance(d, trace.SymDynamics):
+            d.rhs[0] = d.rhs[0] + 0.0 * x[0]            # a picked state inside dynamics: not node-local
+            return d
+        return d + 0.0 * x[0]
+    prob.dynamics = [dyn]
+    prob.backend = "auto"
+    prob.maxIterator = 1
+    out = io.StringIO()
+    with pytest.warns(RuntimeWarning, match="cannot be compiled for the device"):
+        with contextlib.redirect_stdout(out):
+            prob.solve(obj, maxiter=3)
+    assert "node" in prob.fallback_reason and "---- iteration : 1 ----" in out.getvalue()
+    prob.backend = "cuda"                                # the default backend still refuses loudly
+    with pytest.raises(trace.TraceError):
+        with contextlib.redirect_stdout(io.StringIO()):
+            prob.solve(obj, maxiter=1)
