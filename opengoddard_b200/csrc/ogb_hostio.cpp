@@ -113,8 +113,14 @@ void expand_dense(double* dst, size_t nM, const double* vals, const uint32_t* li
     _mm_sfence();
 }
 
+void expand_keep(double* dst, const double* vals, const uint32_t* lin, int nnz);
+
 void expand_keep(double* dst, const double* vals, const uint32_t* lin, int nnz) {
-    for (int e = 0; e < nnz; ++e) dst[lin[e]] = vals[e];
+    const int pf = scatter_prefetch_distance();
+    for (int e = 0; e < nnz; ++e) {
+        if (pf && e + pf < nnz) __builtin_prefetch(dst + lin[e + pf], 1, 0);
+        dst[lin[e]] = vals[e];
+    }
 }
 
 // ---------------------------------------------------------------- worker pool
@@ -138,8 +144,25 @@ struct Job {
 constexpr int kScatterMode = 100;       // internal: ogb_host_eval_fd_scatter
 constexpr int64_t kNowhere = INT64_MIN;
 
+// Scattered 8-byte stores into a matrix that is not in cache: every touched line costs a read-for-ownership
+// miss, and a core only keeps a handful of them in flight on its own.  Prefetching the destination lines a
+// few dozen entries ahead ($OGB200_HOST_PREFETCH, default 48; 0 = off) raises the memory-level parallelism.
+int scatter_prefetch_distance() {
+    static const int d = [] {
+        const char* v = getenv("OGB200_HOST_PREFETCH");
+        const int k = v ? atoi(v) : 48;
+        return k < 0 ? 0 : (k > 1024 ? 1024 : k);
+    }();
+    return d;
+}
+
 void expand_scatter(double* C, double* g, const double* vals, const int64_t* soff, int nnz) {
+    const int pf = scatter_prefetch_distance();
     for (int e = 0; e < nnz; ++e) {
+        if (pf && e + pf < nnz) {
+            const int64_t o2 = soff[e + pf];
+            if (o2 >= 0) __builtin_prefetch(C + o2, 1, 0);
+        }
         const int64_t o = soff[e];
         if (o >= 0) C[o] = vals[e];
         else if (o != kNowhere && g) g[-1 - o] = vals[e];
