@@ -44,6 +44,18 @@ int usable_cores() {
     return std::max(1u, std::thread::hardware_concurrency());
 }
 
+// Scattered 8-byte stores into a matrix that is not in cache: every touched line costs a read-for-ownership
+// miss, and a core only keeps a handful of them in flight on its own.  Prefetching the destination lines a
+// few dozen entries ahead ($OGB200_HOST_PREFETCH, default 48; 0 = off) raises the memory-level parallelism.
+int scatter_prefetch_distance() {
+    static const int d = [] {
+        const char* v = getenv("OGB200_HOST_PREFETCH");
+        const int k = v ? atoi(v) : 48;
+        return k < 0 ? 0 : (k > 1024 ? 1024 : k);
+    }();
+    return d;
+}
+
 int host_isa() {
     // $OGB200_HOST_ISA = 0 / 1 / 2 picks SSE2 / AVX2 / AVX-512 stores.  Default AVX2: one core's
     // non-temporal write rate (~13 GB/s) is the limit either way and 512-bit stores measured slower.
@@ -113,7 +125,7 @@ void expand_dense(double* dst, size_t nM, const double* vals, const uint32_t* li
     _mm_sfence();
 }
 
-void expand_keep(double* dst, const double* vals, const uint32_t* lin, int nnz);
+
 
 void expand_keep(double* dst, const double* vals, const uint32_t* lin, int nnz) {
     const int pf = scatter_prefetch_distance();
@@ -143,18 +155,6 @@ struct Job {
 
 constexpr int kScatterMode = 100;       // internal: ogb_host_eval_fd_scatter
 constexpr int64_t kNowhere = INT64_MIN;
-
-// Scattered 8-byte stores into a matrix that is not in cache: every touched line costs a read-for-ownership
-// miss, and a core only keeps a handful of them in flight on its own.  Prefetching the destination lines a
-// few dozen entries ahead ($OGB200_HOST_PREFETCH, default 48; 0 = off) raises the memory-level parallelism.
-int scatter_prefetch_distance() {
-    static const int d = [] {
-        const char* v = getenv("OGB200_HOST_PREFETCH");
-        const int k = v ? atoi(v) : 48;
-        return k < 0 ? 0 : (k > 1024 ? 1024 : k);
-    }();
-    return d;
-}
 
 void expand_scatter(double* C, double* g, const double* vals, const int64_t* soff, int nnz) {
     const int pf = scatter_prefetch_distance();
