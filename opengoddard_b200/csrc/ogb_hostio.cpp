@@ -46,11 +46,12 @@ int usable_cores() {
 
 // Scattered 8-byte stores into a matrix that is not in cache: every touched line costs a read-for-ownership
 // miss, and a core only keeps a handful of them in flight on its own.  Prefetching the destination lines a
-// few dozen entries ahead ($OGB200_HOST_PREFETCH, default 48; 0 = off) raises the memory-level parallelism.
+// hundred entries ahead ($OGB200_HOST_PREFETCH, default 128; 0 = off) raises the memory-level parallelism
+// (Goddard-50 x 4096 on 16 threads: scatter 18.7 -> 15.1 ms, keep-zeros 18.7 -> 14.0 ms; tools/scatter_probe.py).
 int scatter_prefetch_distance() {
     static const int d = [] {
         const char* v = getenv("OGB200_HOST_PREFETCH");
-        const int k = v ? atoi(v) : 48;
+        const int k = v ? atoi(v) : 128;
         return k < 0 ? 0 : (k > 1024 ? 1024 : k);
     }();
     return d;
