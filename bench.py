@@ -725,7 +725,7 @@ def main():
         e2e_sqp = {"error": str(ex)[:200]}
     sess.close()
     extra = None
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:      # (N = 1 only, like the CPU baseline: the other ranks would idle)
         extra = extras(eng, wl, cfg, workloads, P, P_host, torch, args, api)
 
     if rank == 0:
