@@ -12,6 +12,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """on a machine without a CUDA device the gpu-marked tests are skipped (with the reason), not
+    failed one by one; $OGB200_REQUIRE_GPU=1 turns that back into failures (a GPU box whose driver is broken)."""
+    if os.environ.get("OGB200_REQUIRE_GPU") == "1" or not any("gpu" in it.keywords for it in items):
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this machine (the hot path has no CPU fallback)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def api():
     import OpenGoddard.optimize as mod
