@@ -186,7 +186,9 @@ enum ogb_option {
     OGB_OPT_ZERO_MODE = 12,      /* how the fused kernel writes its zeros (results unchanged): 0 = every warp streams the
                                     zeros of its own column, then overwrites the non-zeros; bit 0 = with st.global.cs
                                     (measured slower); 4 / 8 = one / two dedicated writer warps per CTA stream the
-                                    zeros of the CTA's next work item while the other warps compute                */
+                                    zeros of the CTA's next work item while the other warps compute (measured slower);
+                                    16 = with an odd number of rows a warp takes two adjacent columns and zeroes them
+                                    as one 16-byte-aligned span (no 8-byte stores at the column ends)                 */
     OGB_OPT_GEMM_UNIT = 13,      /* K1 work unit: 0 / 8 (default) = an 8-row tile computes whole rows of D.X; 2 = (8-row tile,
                                     16 output nodes) units (experiment: more warps in flight, measured slower)       */
     OGB_OPT_FUSED_DX = 4         /* 0: K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two launches); 1: the sweep

@@ -31,6 +31,7 @@ struct OgbHostProblem {
     OgbProb P;          // pointer members reference the vectors above (host view)
     OgbPlan plan;            // launch plan of the ahead-of-time (tape-interpreter) sweep kernel
     OgbPlan plan_jit;        // ... of the NVRTC build: the tapes are code there, not shared-memory data
+    int jit_zero_mode = 0;   // OGB_OPT_ZERO_MODE at the time the NVRTC source is generated (compile-time there)
     std::string error;
 
     void bind_host() {

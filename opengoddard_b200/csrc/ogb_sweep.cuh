@@ -108,6 +108,9 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     pl.o_cache = OGB_SPEC_O_CACHE; pl.o_end = OGB_SPEC_O_END; pl.o_gpert = OGB_SPEC_O_GPERT;
 #endif
 #endif
+#ifdef OGB_SPEC_ZMODE                 // NVRTC build: the zero-stream variant is a compile-time choice too, so the
+    zero_mode = OGB_SPEC_ZMODE;       // code of the variants not taken (writer warps, pairs, .cs) is not even compiled
+#endif
     const int tid = threadIdx.x, nthr = blockDim.x;
     // %laneid through a volatile asm: the compiler keeps it in a register instead of re-reading
     // SR_TID.X (an S2R costs ~20 cycles) at every use inside the column loop
@@ -346,12 +349,19 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         auto columns = [&](auto packed_tag) {
             constexpr bool PACKED = decltype(packed_tag)::value;
             constexpr int NRA = NR > 0 ? NR : 1;
-            // dense: J[b, j, :] of the first column of this warp; packed: the instance's values [nnz]
-            double* gdst = PACKED ? J + (size_t)b * (size_t)P.nnz
-                                  : J + (size_t)b * n * (size_t)M + (size_t)(jlo + warp) * (size_t)M;
-            const size_t gstep = PACKED ? 0 : (size_t)cwarps * (size_t)M;
-            const int* pm = PACKED ? P.pmap + (size_t)(jlo + warp) * (size_t)M : nullptr;   // row -> packed entry
-            const size_t pmstep = (size_t)cwarps * (size_t)M;
+            // dense: the item's first column J[b, jlo, :]; packed: the instance's values [nnz]
+            double* const gbase = PACKED ? J + (size_t)b * (size_t)P.nnz
+                                         : J + (size_t)b * n * (size_t)M + (size_t)jlo * (size_t)M;
+            // Work units of the column phase.  Normally one column each.  With an odd number of rows M a column
+            // starts 8 bytes off the 16-byte grid every other time, and its zero stream needs an 8-byte store at
+            // each end (partial sectors, shared with the neighbour column: the fill microbenchmarks lose 13 % to
+            // that).  Pair mode (dense output, M odd, zero_mode bit 4): a warp takes two ADJACENT columns that start
+            // on the 16-byte grid together and zeroes them as ONE aligned span of 2 M doubles, then writes the
+            // non-zeros of both; only a leading / trailing single column of the item keeps an 8-byte end.
+            const bool pairs = !PACKED && (M & 1) && (zero_mode & 16) && with_fd == 1 && !nwr;
+            const int lead = pairs ? (int)((reinterpret_cast<uintptr_t>(gbase) >> 3) & 1) : 0;   // item starts off-grid
+            const int npairs = pairs ? (ncols - lead) / 2 : 0;
+            const int nunits = pairs ? lead + npairs + ((ncols - lead) & 1) : ncols;
             int cur_key = -1, slot_sec = -1;
             double r_sdx[NRA], r_cf[NRA], r_sc[NRA];
             OgbSlot si = {0, 0, 0, 0};               // where this lane's output slot lands (per phase)
@@ -364,7 +374,19 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
             const double* const s_coef = smem + pl.o_coef;
             const int4* const s_pcol = reinterpret_cast<const int4*>(smem + pl.o_pcol);
             const double* const s_sdx = W.sdx;       // (the input stage alternates between items)
-            for (int cc = warp; cc < ncols; cc += cwarps, gdst += gstep, pm += (PACKED ? pmstep : 0)) {
+            for (int u = warp; u < nunits; u += cwarps) {
+              // the unit's first column, how many columns it has, and the length of the zero span it starts
+              int c0 = u, ucols = 1;
+              if (pairs) {
+                  if (u < lead) c0 = 0;
+                  else if (u < lead + npairs) { c0 = lead + 2 * (u - lead); ucols = 2; }
+                  else c0 = ncols - 1;
+              }
+              for (int t = 0; t < ucols; ++t) {
+                const int cc = c0 + t;
+                const int zlen = t == 0 ? ucols * M : 0;             // doubles to zero from this column's start
+                double* gdst = PACKED ? gbase : gbase + (size_t)cc * (size_t)M;
+                const int* pm = PACKED ? P.pmap + (size_t)(jlo + cc) * (size_t)M : nullptr;   // row -> packed entry
                 asm volatile("" : "+l"(gdst));       // keep the column pointer in registers ...
                 __builtin_assume(__isGlobal(gdst));  // ... and its stores in the global space (STG, not ST)
                 // (A) operands
@@ -400,9 +422,9 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 // (B) zeros: 16-byte aligned body, an odd first / last double on its own
                 //     (with_fd == 2: structure probe -- only the overwrites below land, on a
                 //      sentinel-filled J; see ogb_jac_pattern.  3 / 4 / 5: timing probes)
-                if (!PACKED && with_fd != 2 && with_fd != 4 && !nwr) {
+                if (!PACKED && with_fd != 2 && with_fd != 4 && !nwr && zlen) {
                     const unsigned hj = (unsigned)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
-                    const unsigned nbytes = ((unsigned)(M - hj) & ~1u) * 8u;
+                    const unsigned nbytes = ((unsigned)(zlen - hj) & ~1u) * 8u;
                     char* g = reinterpret_cast<char*>(gdst + hj) + lane * 16;
                     const double2 z2 = make_double2(0.0, 0.0);
                     unsigned left = nbytes;                      // bytes not yet covered by the warp
@@ -421,7 +443,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                     if (mine + 1024u < left) *reinterpret_cast<double2*>(g + 1024) = z2;
                     if (mine + 1536u < left) *reinterpret_cast<double2*>(g + 1536) = z2;
                     if (lane == 0 && hj) gdst[0] = 0.0;
-                    if (lane == 1 && ((M - hj) & 1)) gdst[M - 1] = 0.0;
+                    if (lane == 1 && ((zlen - hj) & 1)) gdst[zlen - 1] = 0.0;
                 }
                 __syncwarp();
                 if (!PACKED && with_fd >= 3) continue;   // timing probes: zero stream only / no column output
@@ -497,6 +519,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 } else {
                     ogb_scatter_column(P, W, j, cc, OgbColOut{gdst, gdst + meq, meq}, lane, 32);
                 }
+              }
             }
         };
         if (PACKED_OUT == 2) {
