@@ -45,7 +45,8 @@ struct OgbSec {
     int code_off, ncode, const_off, out_off, nouts, nreg;   // node program
     int run_slot;           // output slot carrying the running-cost integrand, -1 = none
     int nnc, ncoff;         // per-node constant vectors of the node program: count, offset into P.nodec (N doubles each)
-    int ng, goff;           // global variables (final times) the node program reads: count, offset into P.gvars
+    int ng, goff;           // global variables (final times, picked states / controls) the node program reads at every
+                            // node: count, offset into P.gvars
     int pad;
 };
 #ifdef OGB_SPEC_SECTIONS               // NVRTC build: the records are a constant table (see ogb_sec)
@@ -66,9 +67,12 @@ struct OgbCol {             // how Jacobian column j is produced
 
 struct OgbProb {
     int nsec, n, M, meq, mineq, ndx, gtot, nknot, npick, has_running, max_nouts;
-    int any_global;         // some node program reads a final time: those columns recompute whole phases
+    int any_global;         // number of "global columns": decision variables some node program reads at EVERY node (a final
+                            // time, a picked state); their Jacobian columns re-evaluate whole phases (0 = none)
     const double* nodec;    // per-node constant vectors of the node programs
-    const int* gvars;       // global variable indices of the node programs
+    const int* gvars;       // global variable indices of the node programs (per phase, see OgbSec.goff)
+    const int* gcvars;      // [any_global] the distinct global variables, ascending
+    const int* gcol_of;     // [n] variable -> its index in gcvars, or -1
     int sc_code_off, sc_ncode, sc_const_off, sc_out_off, sc_nouts, sc_nreg, sc_cost_slot;
     double unit_time, t0x;  // t0x = time_start(0) / unit_time (optimize.py:683)
     const OgbSec* sec;
@@ -114,8 +118,8 @@ struct OgbWork {            // per work item scratch (shared memory on the devic
     double* rterm;          // [gtot] running-cost terms integrand * w at the base point
     double* costp;          // [G] cost at the perturbed point of each column
     double* prdx;           // [G] 1 / dx, correctly rounded (see ogb_fd_div)
-    double* gpert;          // [nsec][max_nouts][gtot] (only if P.any_global) node-program outputs at every node with
-                            // final time t perturbed (FD) / their tangents (exact), for the phases that read it
+    double* gpert;          // [any_global][max_nouts][gtot] node-program outputs at every node with global variable gi
+                            // perturbed (FD) / their tangents (exact), for the phases that read it
     int G;
 };
 
@@ -560,14 +564,14 @@ __device__ __forceinline__ void ogb_jit_scalar_dual(const OgbProb& P, const Load
 // ------------------------------------------------------------------ phase 2: tape jobs
 // Number of tape jobs of a work item with ncols Jacobian columns (see ogb_job).
 OGB_HD int ogb_njobs(const OgbProb& P, int ncols) {
-    return P.gtot + 1 + ncols + ((ncols > 0 && P.any_global) ? P.nsec * P.gtot : 0);
+    return P.gtot + 1 + ncols + (ncols > 0 ? P.any_global * P.gtot : 0);
 }
 
 // Job q of a work item: q < gtot: node program at base node q; q == gtot: scalar program
 // at the base point + the per-phase time coefficients; gtot < q <= gtot + ncols: Jacobian column
 // jlo + (q - gtot - 1): FD step, perturbed node program, perturbed scalar program; beyond (only when a node
-// program reads a final time): job (t, g) = the node program at node g with final time t perturbed, for the
-// dense column of that final time.
+// program reads a global variable): job (gi, g) = the node program at node g with global variable gi perturbed,
+// for the dense column of that variable.
 OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo, int ncols,
                     const double* lb, const double* ub, double abs_step) {
     if (q < P.gtot) {
@@ -614,8 +618,8 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo, int ncol
         }
     } else {
         const int e = q - (P.gtot + 1 + ncols);
-        const int t = e / P.gtot, g = e - t * P.gtot;
-        const int j = ogb_sec(P, t).tf_idx;
+        const int gi = e / P.gtot, g = e - gi * P.gtot;
+        const int j = P.gcvars[gi];
         if (j < jlo || j >= jlo + ncols) return;      // that column belongs to another work item
         const int s = ogb_sec_of_node(P, g);
         const OgbSec& S = ogb_sec(P, s);
@@ -623,8 +627,11 @@ OGB_HD void ogb_job(const OgbProb& P, const OgbWork& W, int q, int jlo, int ncol
         if (slot < 0) return;
         const double x0 = W.sp[j];
         const double x1 = x0 + ogb_fd_step(x0, lb[j], ub[j], abs_step);
-        const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, g - S.g0, -1, 0.0, slot, x1);
-        OGB_NODE_PROGRAM(s, S, ld, W.gpert + (size_t)t * P.max_nouts * P.gtot + g, P.gtot);
+        // (a picked state / control is also a block input at its own node: perturb both views of it there)
+        const OgbCol col = P.cols[j];
+        const int pblk = (col.sec == s && col.k == g - S.g0) ? col.blk : -1;
+        const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, g - S.g0, pblk, x1, slot, x1);
+        OGB_NODE_PROGRAM(s, S, ld, W.gpert + (size_t)gi * P.max_nouts * P.gtot + g, P.gtot);
     }
 }
 
@@ -686,8 +693,18 @@ OGB_HD void ogb_assemble_cost(const OgbProb& P, const OgbWork& W) {
 // cost at the perturbed point of column cl (one thread per column): the non-integrated
 // part from the perturbed scalar program if the variable is picked, the running sum redone
 // left to right with the one changed term so the rounding matches the reference's sum().
+// the decision variable a column record stands for, and its global-column index (-1: no node program reads it
+// at every node)
+OGB_HD int ogb_col_var(const OgbProb& P, const OgbCol& cd) {
+    if (cd.sec < 0) return ogb_sec(P, cd.blk).tf_idx;
+    const OgbSec& S = ogb_sec(P, cd.sec);
+    return S.off + cd.blk * S.N + cd.k;
+}
+OGB_HD int ogb_col_global(const OgbProb& P, const OgbCol& cd) {
+    return P.any_global ? P.gcol_of[ogb_col_var(P, cd)] : -1;
+}
 OGB_HD bool ogb_col_moves_cost(const OgbProb& P, const OgbCol& cd) {
-    return cd.pick >= 0 || (P.has_running && (cd.sec >= 0 || P.any_global));
+    return cd.pick >= 0 || (P.has_running && (cd.sec >= 0 || ogb_col_global(P, cd) >= 0));
 }
 OGB_HD void ogb_cost_column(const OgbProb& P, const OgbWork& W, int cl) {
     const OgbCol cd = W.pcol[cl];
@@ -695,22 +712,27 @@ OGB_HD void ogb_cost_column(const OgbProb& P, const OgbWork& W, int cl) {
     double cost = cd.pick >= 0 ? W.scpert[P.sc_cost_slot * P.npick + cd.pick] : W.scbase[P.sc_cost_slot];
     if (P.has_running) {
         double acc = W.prefix[P.gtot];
-        if (cd.sec >= 0) {
-            const OgbSec& S = ogb_sec(P, cd.sec);
-            const int g = S.g0 + cd.k;
-            acc = W.prefix[g] + W.pert[S.run_slot * W.G + cl] * P.w[g];
-            for (int g2 = g + 1; g2 < P.gtot; ++g2) acc += W.rterm[g2];
-        } else if (P.any_global) {
-            // a final time the integrand may read: the whole sum again, left to right, with the re-evaluated
-            // terms of the phases that read it
-            const int t = cd.blk, j = ogb_sec(P, t).tf_idx;
+        const int gi = ogb_col_global(P, cd);
+        if (gi >= 0) {
+            // a variable the integrand may read at every node: the whole sum again, left to right, with the
+            // re-evaluated terms of the phases that read it (and the one changed node of its own phase otherwise)
+            const int j = ogb_col_var(P, cd);
             acc = 0.0;
             for (int s = 0; s < P.nsec; ++s) {
                 const OgbSec& S = ogb_sec(P, s);
                 const bool reads = ogb_global_slot(P, S, j) >= 0;
-                const double* gp = W.gpert + ((size_t)t * P.max_nouts + S.run_slot) * P.gtot;
-                for (int g = S.g0; g < S.g0 + S.N; ++g) acc += reads ? gp[g] * P.w[g] : W.rterm[g];
+                const double* gp = W.gpert + ((size_t)gi * P.max_nouts + S.run_slot) * P.gtot;
+                for (int g = S.g0; g < S.g0 + S.N; ++g) {
+                    if (reads) acc += gp[g] * P.w[g];
+                    else if (cd.sec == s && g == S.g0 + cd.k) acc += W.pert[S.run_slot * W.G + cl] * P.w[g];
+                    else acc += W.rterm[g];
+                }
             }
+        } else if (cd.sec >= 0) {
+            const OgbSec& S = ogb_sec(P, cd.sec);
+            const int g = S.g0 + cd.k;
+            acc = W.prefix[g] + W.pert[S.run_slot * W.G + cl] * P.w[g];
+            for (int g2 = g + 1; g2 < P.gtot; ++g2) acc += W.rterm[g2];
         }
         cost = cost + acc;
     }
@@ -793,29 +815,36 @@ OGB_HD void ogb_scatter_knots(const OgbProb& P, const OgbWork& W, int j, double 
     }
 }
 
-// a final-time variable: the defects of its own phase and of the next one rescale; phases whose node program
-// reads it (non-autonomous dynamics, time-dependent path rows) are re-evaluated at every node (W.gpert)
+// The phases a column moves as a whole: for a final-time column the defects of its own phase and of the next one
+// rescale ((t_f - t_0) / 2 changes); for any variable a node program reads at every node (a final time in
+// non-autonomous dynamics, a picked state) the reading phases are re-evaluated at every node (W.gpert).  For a
+// state column of a reading phase the D-block term D[i, k] * delta is folded in here as well (the local code
+// does not run for that phase).
 template <class Out>
-OGB_HD void ogb_scatter_time(const OgbProb& P, const OgbWork& W, int j, int sec, double x1, double dx,
-                             double rdx, const Out& col, int lane, int nlanes) {
+OGB_HD void ogb_scatter_phases(const OgbProb& P, const OgbWork& W, int j, const OgbCol& cd, int gi, double x1,
+                               double dlt, double dx, double rdx, const Out& col, int lane, int nlanes) {
     const double tfx1 = ogb_nd(x1, P.unit_time);
-    const int slo = P.any_global ? 0 : sec, shi = P.any_global ? P.nsec : (sec + 2 < P.nsec ? sec + 2 : P.nsec);
-    for (int s = slo; s < shi; ++s) {
+    const int tsec = cd.sec < 0 ? cd.blk : -1;                   // the phase whose final time this column is
+    for (int s = 0; s < P.nsec; ++s) {
         const OgbSec& S = ogb_sec(P, s);
-        const bool reads = P.any_global && ogb_global_slot(P, S, j) >= 0;
+        const bool reads = gi >= 0 && ogb_global_slot(P, S, j) >= 0;
         double coef1 = W.coef[3 * s];
         bool moved = reads;
-        if (s == sec) { coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0; moved = true; }
-        else if (S.t0_idx == j) { coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0; moved = true; }
+        if (s == tsec) { coef1 = (tfx1 - W.coef[3 * s + 2]) / 2.0; moved = true; }
+        else if (tsec >= 0 && S.t0_idx == j) { coef1 = (W.coef[3 * s + 1] - tfx1) / 2.0; moved = true; }
         if (!moved) continue;
-        const double* f1 = reads ? W.gpert + (size_t)sec * P.max_nouts * P.gtot : W.sbase;
+        const double* f1 = reads ? W.gpert + (size_t)gi * P.max_nouts * P.gtot : W.sbase;
+        const int a = (cd.sec == s && cd.blk < S.ns) ? cd.blk : -1;            // a state column of this phase
+        const double* Dt = P.Dt + S.doff + (a >= 0 ? cd.k : 0) * S.N;         // column k of D
         for (int e = lane; e < S.ns * S.N; e += nlanes) {
             const int b = e / S.N, i = e - b * S.N;
-            const double cp = W.sdx[S.dxoff + e] - coef1 * f1[b * P.gtot + S.g0 + i];
+            double dxp = W.sdx[S.dxoff + e];
+            if (b == a) dxp = dxp + Dt[i] * dlt;
+            const double cp = dxp - coef1 * f1[b * P.gtot + S.g0 + i];
             col.put(S.rdef + e, ogb_fd_div(cp - W.sc[S.rdef + e], dx, rdx));
         }
         if (!reads) continue;
-        for (int slot = S.ns; slot < S.nouts; ++slot) {          // pointwise user rows that read the final time
+        for (int slot = S.ns; slot < S.nouts; ++slot) {          // pointwise user rows of a reading phase
             const ogb_out o = P.outs[S.out_off + slot];
             if (o.kind != OGB_OUT_EQ_POINT && o.kind != OGB_OUT_INEQ_POINT) continue;
             for (int k = lane; k < S.N; k += nlanes) {
@@ -849,16 +878,18 @@ OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl
     const OgbCol cd = W.pcol[cl];
     const double dx = W.pdx[cl], rdx = W.prdx[cl];
     const double x1 = W.px1[cl];
+    const int gi = ogb_col_global(P, cd);
+    const double dlt = cd.sec >= 0 ? W.pdlt[cl] : 0.0;
     if (cd.sec >= 0) {
         const OgbSec& S = ogb_sec(P, cd.sec);
-        const double dlt = W.pdlt[cl];
-        const int a = cd.blk < S.ns ? cd.blk : -1;
-        if (a >= 0) ogb_scatter_drows(P, W, S, a, cd.k, dlt, dx, rdx, col, lane, nlanes);
-        ogb_scatter_noderows(P, W, S, cd.sec, a, cd.k, cl, dlt, dx, rdx, col, lane, nlanes);
+        if (!(gi >= 0 && ogb_global_slot(P, S, j) >= 0)) {       // (a phase that reads j at every node: below)
+            const int a = cd.blk < S.ns ? cd.blk : -1;
+            if (a >= 0) ogb_scatter_drows(P, W, S, a, cd.k, dlt, dx, rdx, col, lane, nlanes);
+            ogb_scatter_noderows(P, W, S, cd.sec, a, cd.k, cl, dlt, dx, rdx, col, lane, nlanes);
+        }
         if (P.nknot) ogb_scatter_knots(P, W, j, x1, dx, rdx, col, lane, nlanes);
-    } else {
-        ogb_scatter_time(P, W, j, cd.blk, x1, dx, rdx, col, lane, nlanes);
     }
+    if (cd.sec < 0 || gi >= 0) ogb_scatter_phases(P, W, j, cd, gi, x1, dlt, dx, rdx, col, lane, nlanes);
     ogb_scatter_scalar_cost(P, W, cd, cl, dx, rdx, col, lane, nlanes);
 }
 
@@ -874,6 +905,7 @@ OGB_HD void ogb_scatter_column(const OgbProb& P, const OgbWork& W, int j, int cl
 // (reference rows: optimize.py:670-709; (p * unit) / unit has derivative 1).  The tangents come from the
 // traced tapes run in dual arithmetic (ogb_run_tape_dual / the NVRTC-generated dual programs).
 
+#define OGB_MAX_GLOBAL_OUTS 64       // output slots of a node program that reads a picked state / control (host-checked)
 // Job q of a work item in exact mode: q <= gtot as in ogb_job; q > gtot: tangents of column jlo + (q - gtot - 1)
 OGB_HD void ogb_job_exact(const OgbProb& P, const OgbWork& W, int q, int jlo, int ncols) {
     if (q <= P.gtot) { ogb_job(P, W, q, jlo, ncols, nullptr, nullptr, 0.0); return; }
@@ -893,16 +925,25 @@ OGB_HD void ogb_job_exact(const OgbProb& P, const OgbWork& W, int q, int jlo, in
         }
         return;
     }
-    const int e = q - (P.gtot + 1 + ncols);              // tangents with respect to a final time, at every node
-    const int t = e / P.gtot, g = e - t * P.gtot;
-    const int j = ogb_sec(P, t).tf_idx;
+    const int e = q - (P.gtot + 1 + ncols);              // tangents with respect to a global variable, at every node
+    const int gi = e / P.gtot, g = e - gi * P.gtot;
+    const int j = P.gcvars[gi];
     if (j < jlo || j >= jlo + ncols) return;
     const int s = ogb_sec_of_node(P, g);
     const OgbSec& S = ogb_sec(P, s);
     const int slot = ogb_global_slot(P, S, j);
     if (slot < 0) return;
     const OgbNodeLoad ld = ogb_node_load(P, W.sp, S, g - S.g0, -1, 0.0);
-    OGB_NODE_PROGRAM_DUAL(s, S, ld, S.nb + S.nnc + slot, W.gpert + (size_t)t * P.max_nouts * P.gtot + g, P.gtot);
+    double* out = W.gpert + (size_t)gi * P.max_nouts * P.gtot + g;
+    OGB_NODE_PROGRAM_DUAL(s, S, ld, S.nb + S.nnc + slot, out, P.gtot);
+    // a picked state / control is also a block input at its own node: the total derivative there is the sum of
+    // the tangents along both views (the column job has the block tangent in W.pert)
+    const OgbCol col = P.cols[j];
+    if (col.sec == s && col.k == g - S.g0) {
+        double tmp[OGB_MAX_GLOBAL_OUTS];
+        OGB_NODE_PROGRAM_DUAL(s, S, ld, col.blk, tmp, 1);
+        for (int t = 0; t < S.nouts; ++t) out[(size_t)t * P.gtot] += tmp[t];
+    }
 }
 
 // d cost / d x_j of column cl (one thread per column)
@@ -910,17 +951,21 @@ OGB_HD void ogb_cost_column_exact(const OgbProb& P, const OgbWork& W, int cl) {
     const OgbCol cd = W.pcol[cl];
     if (!ogb_col_moves_cost(P, cd)) return;
     double g = cd.pick >= 0 ? W.scpert[P.sc_cost_slot * P.npick + cd.pick] : 0.0;
-    if (P.has_running && cd.sec >= 0) {
-        const OgbSec& S = ogb_sec(P, cd.sec);
-        g = g + W.pert[S.run_slot * W.G + cl] * P.w[S.g0 + cd.k];
-    } else if (P.has_running && P.any_global) {
-        const int t = cd.blk, j = ogb_sec(P, t).tf_idx;
+    const int gi = ogb_col_global(P, cd);
+    if (P.has_running && gi >= 0) {
+        const int j = ogb_col_var(P, cd);
         for (int s = 0; s < P.nsec; ++s) {
             const OgbSec& S = ogb_sec(P, s);
-            if (ogb_global_slot(P, S, j) < 0) continue;
-            const double* gp = W.gpert + ((size_t)t * P.max_nouts + S.run_slot) * P.gtot;
-            for (int q = S.g0; q < S.g0 + S.N; ++q) g = g + gp[q] * P.w[q];
+            if (ogb_global_slot(P, S, j) >= 0) {
+                const double* gp = W.gpert + ((size_t)gi * P.max_nouts + S.run_slot) * P.gtot;
+                for (int q = S.g0; q < S.g0 + S.N; ++q) g = g + gp[q] * P.w[q];
+            } else if (cd.sec == s) {
+                g = g + W.pert[S.run_slot * W.G + cl] * P.w[S.g0 + cd.k];
+            }
         }
+    } else if (P.has_running && cd.sec >= 0) {
+        const OgbSec& S = ogb_sec(P, cd.sec);
+        g = g + W.pert[S.run_slot * W.G + cl] * P.w[S.g0 + cd.k];
     }
     W.costp[cl] = g;
 }
@@ -948,60 +993,71 @@ OGB_HD void ogb_scatter_scalar_cost_exact(const OgbProb& P, const OgbWork& W, co
     if (lane == 0 && ogb_col_moves_cost(P, cd)) col.put(P.M - 1, W.costp[cl]);
 }
 
+// exact counterpart of ogb_scatter_phases: d/dx_j of the rows of the phases the column moves as a whole
+template <class Out>
+OGB_HD void ogb_scatter_phases_exact(const OgbProb& P, const OgbWork& W, int j, const OgbCol& cd, int gi,
+                                     const Out& col, int lane, int nlanes) {
+    const int tsec = cd.sec < 0 ? cd.blk : -1;
+    for (int s = 0; s < P.nsec; ++s) {
+        const OgbSec& S = ogb_sec(P, s);
+        const bool reads = gi >= 0 && ogb_global_slot(P, S, j) >= 0;
+        double sign = 0.0;                               // -d coef_s / d x_j
+        if (s == tsec) sign = -0.5;
+        else if (tsec >= 0 && S.t0_idx == j) sign = 0.5;
+        else if (!reads) continue;
+        const double coef = W.coef[3 * s];
+        const double* tg = W.gpert + (size_t)(gi >= 0 ? gi : 0) * P.max_nouts * P.gtot;   // tangents, if the phase reads x_j
+        const int a = (cd.sec == s && cd.blk < S.ns) ? cd.blk : -1;
+        const double* Dt = P.Dt + S.doff + (a >= 0 ? cd.k : 0) * S.N;
+        for (int e = lane; e < S.ns * S.N; e += nlanes) {
+            const int b = e / S.N, i = e - b * S.N;
+            double v = sign * W.sbase[b * P.gtot + S.g0 + i];
+            if (b == a) v = v + Dt[i];
+            if (reads) v = v - coef * tg[b * P.gtot + S.g0 + i];
+            col.put(S.rdef + e, v);
+        }
+        if (!reads) continue;
+        for (int slot = S.ns; slot < S.nouts; ++slot) {
+            const ogb_out o = P.outs[S.out_off + slot];
+            if (o.kind != OGB_OUT_EQ_POINT && o.kind != OGB_OUT_INEQ_POINT) continue;
+            for (int k = lane; k < S.N; k += nlanes) {
+                const int g = S.g0 + k;
+                if (g >= o.glo && g < o.ghi) col.put(o.row + (g - o.glo), tg[slot * P.gtot + g]);
+            }
+        }
+    }
+}
+
 template <class Out>
 OGB_HD void ogb_scatter_column_exact(const OgbProb& P, const OgbWork& W, int j, int cl, const Out& col,
                                      int lane, int nlanes) {
     const OgbCol cd = W.pcol[cl];
+    const int gi = ogb_col_global(P, cd);
     if (cd.sec >= 0) {
         const OgbSec& S = ogb_sec(P, cd.sec);
-        const int k = cd.k, a = cd.blk < S.ns ? cd.blk : -1;
-        const double coef = W.coef[3 * cd.sec];
-        if (a >= 0) {
-            const double* Dt = P.Dt + S.doff + k * S.N;            // column k of D
-            for (int i = lane; i < S.N; i += nlanes)
-                if (i != k) col.put(S.rdef + a * S.N + i, Dt[i]);
-        }
-        const int g = S.g0 + k;
-        for (int slot = lane; slot < S.nouts; slot += nlanes) {
-            const double t = W.pert[slot * W.G + cl];
-            if (slot < S.ns) {
-                const double dkk = slot == a ? P.D[S.doff + k * S.N + k] : 0.0;
-                col.put(S.rdef + slot * S.N + k, dkk - coef * t);
-            } else {
-                const ogb_out o = P.outs[S.out_off + slot];
-                if ((o.kind == OGB_OUT_EQ_POINT || o.kind == OGB_OUT_INEQ_POINT) && g >= o.glo && g < o.ghi)
-                    col.put(o.row + (g - o.glo), t);
+        if (!(gi >= 0 && ogb_global_slot(P, S, j) >= 0)) {
+            const int k = cd.k, a = cd.blk < S.ns ? cd.blk : -1;
+            const double coef = W.coef[3 * cd.sec];
+            if (a >= 0) {
+                const double* Dt = P.Dt + S.doff + k * S.N;            // column k of D
+                for (int i = lane; i < S.N; i += nlanes)
+                    if (i != k) col.put(S.rdef + a * S.N + i, Dt[i]);
             }
-        }
-        ogb_scatter_knots_exact(P, j, col, lane, nlanes);
-    } else {
-        const int sec = cd.blk;
-        const int slo = P.any_global ? 0 : sec, shi = P.any_global ? P.nsec : (sec + 2 < P.nsec ? sec + 2 : P.nsec);
-        for (int s = slo; s < shi; ++s) {
-            const OgbSec& S = ogb_sec(P, s);
-            const bool reads = P.any_global && ogb_global_slot(P, S, j) >= 0;
-            double sign = 0.0;                           // -d coef_s / d t_f
-            if (s == sec) sign = -0.5;
-            else if (S.t0_idx == j) sign = 0.5;
-            else if (!reads) continue;
-            const double coef = W.coef[3 * s];
-            const double* tg = W.gpert + (size_t)sec * P.max_nouts * P.gtot;     // tangents, if the phase reads t_f
-            for (int e = lane; e < S.ns * S.N; e += nlanes) {
-                const int b = e / S.N, i = e - b * S.N;
-                double v = sign * W.sbase[b * P.gtot + S.g0 + i];
-                if (reads) v = v - coef * tg[b * P.gtot + S.g0 + i];
-                col.put(S.rdef + e, v);
-            }
-            if (!reads) continue;
-            for (int slot = S.ns; slot < S.nouts; ++slot) {
-                const ogb_out o = P.outs[S.out_off + slot];
-                if (o.kind != OGB_OUT_EQ_POINT && o.kind != OGB_OUT_INEQ_POINT) continue;
-                for (int k = lane; k < S.N; k += nlanes) {
-                    const int g = S.g0 + k;
-                    if (g >= o.glo && g < o.ghi) col.put(o.row + (g - o.glo), tg[slot * P.gtot + g]);
+            const int g = S.g0 + k;
+            for (int slot = lane; slot < S.nouts; slot += nlanes) {
+                const double t = W.pert[slot * W.G + cl];
+                if (slot < S.ns) {
+                    const double dkk = slot == a ? P.D[S.doff + k * S.N + k] : 0.0;
+                    col.put(S.rdef + slot * S.N + k, dkk - coef * t);
+                } else {
+                    const ogb_out o = P.outs[S.out_off + slot];
+                    if ((o.kind == OGB_OUT_EQ_POINT || o.kind == OGB_OUT_INEQ_POINT) && g >= o.glo && g < o.ghi)
+                        col.put(o.row + (g - o.glo), t);
                 }
             }
         }
+        ogb_scatter_knots_exact(P, j, col, lane, nlanes);
     }
+    if (cd.sec < 0 || gi >= 0) ogb_scatter_phases_exact(P, W, j, cd, gi, col, lane, nlanes);
     ogb_scatter_scalar_cost_exact(P, W, cd, cl, col, lane, nlanes);
 }

@@ -22,7 +22,7 @@ struct OgbHostProblem {
     std::vector<ogb_out> outs;
     std::vector<uint64_t> code;
     std::vector<double> consts, D, Dt, w, tau, ustate, ucontrol, nodec;
-    std::vector<int> gvars;
+    std::vector<int> gvars, gcvars, gcol_of;
     std::vector<OgbKnot> knots;
     std::vector<OgbCol> cols;
     std::vector<int> pickvars;
@@ -38,7 +38,7 @@ struct OgbHostProblem {
         P.sec = sec.data(); P.outs = outs.data(); P.code = code.data(); P.consts = consts.data();
         P.D = D.data(); P.Dt = Dt.data(); P.w = w.data(); P.ustate = ustate.data();
         P.tau = tau.data(); P.ucontrol = ucontrol.data();
-        P.nodec = nodec.data(); P.gvars = gvars.data();
+        P.nodec = nodec.data(); P.gvars = gvars.data(); P.gcvars = gcvars.data(); P.gcol_of = gcol_of.data();
         P.knots = knots.data(); P.cols = cols.data(); P.pickvars = pickvars.data();
         P.tables = tables.data(); P.tab_x = tab_x.data(); P.tab_y = tab_y.data();
     }
@@ -96,7 +96,7 @@ static inline void ogb_layout(const OgbProb& P, size_t ncode, size_t nconsts, si
     pl->o_costp = o;   o += ogb_even(pl->G);
     pl->o_prdx = o;    o += ogb_even(pl->G);
     pl->o_slot = o;    o += nouts * 2;                     // int4 per output slot
-    pl->o_gpert = o;   o += P.any_global ? ogb_even((size_t)P.nsec * P.max_nouts * P.gtot) : 0;
+    pl->o_gpert = o;   o += ogb_even((size_t)P.any_global * P.max_nouts * P.gtot);
     pl->o_tiles = pl->o_tail = o;                          // (no column staging: J is written directly)
     pl->tile_stride = pl->tail_stride = 0;
     pl->o_end = o;
@@ -290,10 +290,11 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
         S.ng = pr.nglobals; S.goff = (int)H->gvars.size();
         for (int i = 0; i < pr.nglobals; ++i) {
             const int v = pr.globals_h[i];
-            if (v < P.n - d->nsec || v >= P.n) { delete H; return fail("a node program may only read final times as global variables"); }
+            if (v < 0 || v >= P.n) { delete H; return fail("a node program's global variable is outside the decision vector"); }
+            if (v < P.n - d->nsec && pr.nouts > OGB_MAX_GLOBAL_OUTS) { delete H; return fail("a node program that reads a picked state / control has too many outputs"); }
             H->gvars.push_back(v);
+            H->gcvars.push_back(v);
         }
-        if (pr.nglobals > 0) P.any_global = 1;
         for (int i = 0; i < pr.ncode; ++i)
             if ((int)(pr.code_h[i] >> 56) == OGB_LDP && (int)((pr.code_h[i] >> 28) & 0x3fff) >= S.nb + S.nnc + S.ng) { delete H; return fail("node program reads an input outside the phase's blocks, constants and globals"); }
         if (d->has_running_cost && S.run_slot < 0) { delete H; return fail("running cost declared but a phase has no integrand output"); }
@@ -331,7 +332,13 @@ static inline OgbHostProblem* ogb_build_host_problem(const ogb_problem_desc* d, 
     for (int i = 0; i < P.npick; ++i) H->cols[H->pickvars[i]].pick = i;
     if (H->pickvars.empty()) H->pickvars.push_back(0);   // keep the device array non-empty
     if (H->nodec.empty()) H->nodec.push_back(0.0);
+    std::sort(H->gcvars.begin(), H->gcvars.end());
+    H->gcvars.erase(std::unique(H->gcvars.begin(), H->gcvars.end()), H->gcvars.end());
+    P.any_global = (int)H->gcvars.size();
+    H->gcol_of.assign((size_t)P.n, -1);
+    for (int i = 0; i < P.any_global; ++i) H->gcol_of[H->gcvars[i]] = i;
     if (H->gvars.empty()) H->gvars.push_back(0);
+    if (H->gcvars.empty()) H->gcvars.push_back(0);
 
     H->bind_host();
     if (!ogb_make_plan(P, H->code.size(), H->consts.size(), H->outs.size(), &H->plan, err)) { delete H; return nullptr; }

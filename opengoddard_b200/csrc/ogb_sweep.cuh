@@ -393,7 +393,7 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 const int4 cdv = s_pcol[cc];
                 const OgbCol cd = {cdv.x, cdv.y, cdv.z, cdv.w};
                 const double dx = s_pdx[cc], rdx = s_prdx[cc];
-                const bool fcol = fast && cd.sec >= 0;
+                const bool fcol = fast && cd.sec >= 0 && !(P.any_global && P.gcol_of[jlo + cc] >= 0);
                 double dlt = 0.0, pv = 0.0, dkk = 0.0, coef = 0.0;
                 double dtv[NRA];
 #pragma unroll
@@ -538,7 +538,10 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
                 const int4 cdv = s_pcol[cc];
                 const OgbCol cd = {cdv.x, cdv.y, cdv.z, cdv.w};
                 const OgbColPacked col{vb, pm};
-                if (!(fast && cd.sec >= 0)) { ogb_scatter_column_exact(P, W, j, cc, col, lane, 32); continue; }
+                if (!(fast && cd.sec >= 0) || (P.any_global && P.gcol_of[j] >= 0)) {
+                    ogb_scatter_column_exact(P, W, j, cc, col, lane, 32);
+                    continue;
+                }
                 const OgbSec& S = ogb_sec(P, cd.sec);
                 const int N = S.N, k = cd.k, a = cd.blk < S.ns ? cd.blk : -1;
                 if (cd.sec != slot_sec) {

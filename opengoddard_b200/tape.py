@@ -135,12 +135,14 @@ class ProblemIR:
     unit_controls: list = field(default_factory=list)   # flattened over phases (guess / trajectory kernels only)
 
 
-def _node_local(ctx, leaf, s):
+def _node_local(ctx, leaf, s, any_var=False):
     """May a node program of phase s read this leaf?  The phase's own blocks and per-node constants at the
-    node, and the final times (global: every node reads the same value; their Jacobian columns are dense)."""
+    node, and global variables every node reads alike (their Jacobian columns are dense in the phase): the
+    final times -- and, for dynamics / running cost (any_var), picked states / controls such as `m[0]`.  User
+    rows that mix a vector with a picked element keep being expanded into scalar rows instead (sparser)."""
     if leaf[0] in ("blk", "nodec"):
         return leaf[1] == s
-    return leaf[0] == "var" and ctx.is_time_var(leaf[1])
+    return leaf[0] == "var" and (any_var or ctx.is_time_var(leaf[1]))
 
 
 class _RowBuilder:
@@ -225,11 +227,12 @@ def _build_ir(prob, obj):
                 else:
                     raise T.TraceError("dynamics[%d] of phase %d is not a vector over that phase's nodes" % (a, s))
                 for lf in T.leaves(node):
-                    if not _node_local(ctx, lf, s):
+                    if not _node_local(ctx, lf, s, any_var=True):
                         raise T.TraceError("dynamics of phase %d reads %r: on the device a dynamics function may read "
                                            "that phase's states / controls at the same node, per-node constants "
-                                           "(prob.time[s], prob.tau[s], tables of one value per node) and the final "
-                                           "times -- not other nodes or phases" % (s, lf))
+                                           "(prob.time[s], prob.tau[s], tables of one value per node), the final "
+                                           "times and picked elements (x[0], m[-1]) -- not whole vectors of other "
+                                           "nodes or phases" % (s, lf))
             else:
                 arr = np.atleast_1d(np.asarray(it, dtype=float))
                 if np.all(arr == arr.flat[0]):
@@ -266,7 +269,7 @@ def _build_ir(prob, obj):
             raise T.TraceError("running_cost() must return one value per node of every phase")
         for s, p in rres.parts.items():
             for lf in T.leaves(p):
-                if not _node_local(ctx, lf, s):
+                if not _node_local(ctx, lf, s, any_var=True):
                     raise T.TraceError("running_cost() must be pointwise in the node")
         run_parts = rres.parts
 

@@ -996,3 +996,66 @@ def nonautonomous(api, nodes=(11, 8)):
 
 CONFIGS["edge_nonautonomous"] = (nonautonomous, (11, 8))
 CONFIGS["edge_nonautonomous_big"] = (nonautonomous, (40, 33))
+
+
+def picked_dynamics(api, nodes=(9, 12)):
+    """Edge case: the dynamics and the running cost read PICKED elements of the decision vector at every node --
+    the phase's own initial state (`v[0]`, the way a mass ratio m / m[0] appears), its last control value, an
+    element of the OTHER phase -- next to the final time.  Legal in the reference (eager evaluation,
+    optimize.py:685); on the device these variables become global inputs of the node programs and their Jacobian
+    columns are dense in the phases that read them."""
+    class Obj:
+        k = 0.35
+
+    obj = Obj()
+    prob = api.Problem([0.0, 1.0, 2.5], list(nodes), [2, 2], [1, 1], 5)
+    prob.set_unit_states_all_section(0, 3.0)
+    prob.set_unit_controls_all_section(0, 0.5)
+
+    def dyn(prob, obj, section):
+        x = prob.states(0, section)
+        v = prob.states(1, section)
+        u = prob.controls(0, section)
+        v0 = v[0]                                     # picked: this phase's first node
+        uN = u[-1]                                    # picked control: this phase's last node
+        other = prob.states(0, 1 - section)[2]        # picked: an element of the other phase
+        d = api.Dynamics(prob, section)
+        d[0] = v * (1.0 + 0.1 * np.sin(v0)) + 0.05 * other
+        d[1] = u - obj.k * v / (1.0 + v0 ** 2) + 0.02 * uN * x / prob.time_final(section)
+        return d()
+
+    def eq(prob, obj):
+        r = api.Condition()
+        r.equal(prob.states(0, 0)[0], 0.0)
+        r.equal(prob.states(1, 0)[0], 0.4)
+        r.equal(prob.states(0, 1)[-1], 2.0)
+        return r()
+
+    def ineq(prob, obj):
+        r = api.Condition()
+        r.upper_bound(prob.controls_all_section(0), 2.0)
+        r.lower_bound(prob.states_all_section(1), -1.0)
+        return r()
+
+    def running(prob, obj):
+        u = prob.controls_all_section(0)
+        return u ** 2 * (1.0 + 0.3 * prob.states(1, 0)[0])
+
+    def cost(prob, obj):
+        return prob.time_final(-1)
+
+    t = prob.time_all_section
+    G = api.Guess
+    prob.set_states_all_section(0, G.linear(t, 0.0, 2.0))
+    prob.set_states_all_section(1, G.cubic(t, 0.4, 0.3, 0.9, -0.2))
+    prob.set_controls_all_section(0, G.linear(t, 0.7, -0.1))
+    prob.dynamics = [dyn, dyn]
+    prob.knot_states_smooth = [True]
+    prob.cost = cost
+    prob.running_cost = running
+    prob.equality = eq
+    prob.inequality = ineq
+    return Workload("picked_dynamics", prob, obj, None)
+
+
+CONFIGS["edge_picked_dynamics"] = (picked_dynamics, (9, 12))

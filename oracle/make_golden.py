@@ -50,6 +50,7 @@ WORKLOAD_INSTANCES = {
     "ex09_polar_tsto20x2": 2,
     "ex10_lowthrust100": 1,
     "edge_nonautonomous": 2,
+    "edge_picked_dynamics": 2,
 }
 
 

@@ -19,7 +19,7 @@ FD_VS_EXACT_RTOL = 1e-4      # the forward-difference Jacobian against the exact
 
 CFGS = ["cfg1_brachistochrone20", "cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40",
         "cfg5_lowthrust128", "ex09_polar_tsto20x2", "edge_table_lookup", "edge_all_ops", "edge_nonautonomous",
-        "edge_nonautonomous_big"]
+        "edge_nonautonomous_big", "edge_picked_dynamics"]
 
 
 def oracle_jacobian(wo, x, lb, ub):

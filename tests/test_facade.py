@@ -311,22 +311,31 @@ def test_time_dependent_callbacks_trace_to_node_programs(api):
 
 
 def test_non_local_dynamics_are_refused_with_a_clear_message(api):
-    """VERDICT r1 probes, unsupported on the device (the reference accepts them because it evaluates eagerly):
-    a reversed vector, a picked state and another phase's block inside `dynamics` raise TraceError -- loudly,
-    never a silently different problem."""
-    for what in ("reversed", "picked", "other_phase"):
+    """VERDICT r1 probes.  Supported since round 2: picked elements (`h[0]`, an element of another phase) inside
+    `dynamics` -- they become global inputs of the node program.  Still unsupported on the device (the reference
+    accepts them because it evaluates eagerly): a reversed vector and another phase's WHOLE block raise
+    TraceError -- loudly, never a silently different problem."""
+    for what in ("picked", "picked_other_phase"):
+        prob, obj = _two_phase(api)
+        base = prob.dynamics[0]
+
+        def dyn(p, o, s, what=what):
+            d = base(p, o, s)
+            d.rhs[0] = d.rhs[0] + (p.states(0, s)[0] if what == "picked" else p.states(0, 1 - s)[3])
+            return d
+        prob.dynamics = [dyn, dyn]
+        ir = tape.build_ir(prob, obj)
+        N = prob.nodes[0]
+        want = [[0], [prob.index_states(0, 1, 0)]] if what == "picked" else [[prob.index_states(0, 1, 3)], [3]]
+        assert [t.globals for t in ir.node_tapes] == want
+    for what in ("reversed", "other_phase"):
         prob, obj = _two_phase(api)
         base = prob.dynamics[0]
 
         def dyn(p, o, s, what=what):
             d = base(p, o, s)
             h = p.states(0, s)
-            if what == "reversed":
-                d.rhs[0] = d.rhs[0] + h[::-1]
-            elif what == "picked":
-                d.rhs[0] = d.rhs[0] + h[0]
-            else:
-                d.rhs[0] = d.rhs[0] + p.states(0, 1 - s)
+            d.rhs[0] = d.rhs[0] + (h[::-1] if what == "reversed" else p.states(0, 1 - s))
             return d
         prob.dynamics = [dyn, dyn]
         with pytest.raises((trace.TraceError, ValueError)) as ei:
@@ -347,9 +356,9 @@ def test_backend_auto_falls_back_per_problem_with_a_warning(api, monkeypatch):
         d = base(p, o, s)
         x = p.states(0, s)
         if isinstance(d, trace.SymDynamics):
-            d.rhs[0] = d.rhs[0] + 0.0 * x[0]            # a picked state inside dynamics: not node-local
+            d.rhs[0] = d.rhs[0] + 0.0 * x[::-1]         # a reversed vector inside dynamics: not node-local
             return d
-        return d + 0.0 * x[0]
+        return d + np.concatenate([0.0 * x[::-1], np.zeros(2 * len(x))])
     prob.dynamics = [dyn]
     prob.backend = "auto"
     prob.maxIterator = 1

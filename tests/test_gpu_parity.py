@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 CFGS = ["cfg1_brachistochrone20", "cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40",
         "cfg5_lowthrust128", "ex05_goddard_knot25x2", "ex09_polar_tsto20x2", "ex10_lowthrust100",
-        "edge_nonautonomous"]
+        "edge_nonautonomous", "edge_picked_dynamics"]
 
 
 @pytest.fixture(scope="module")
@@ -50,7 +50,7 @@ def test_eval_fd_vs_reference_golden(torch_cuda, api, name):
 
 @pytest.mark.parametrize("name", ["cfg3_goddard_knot30x2", "cfg4_polar3x40", "cfg5_lowthrust128",
                                   "edge_table_lookup", "edge_stress_mixed", "edge_all_ops", "edge_nonautonomous",
-                                  "edge_nonautonomous_big"])
+                                  "edge_nonautonomous_big", "edge_picked_dynamics"])
 def test_jit_and_interpreter_kernels_agree(torch_cuda, api, name):
     from opengoddard_b200 import workloads
     wl = workloads.build(name, api)

@@ -55,7 +55,7 @@ def test_host_stats_layout():
 # ------------------------------------------------------------------ GPU: the session
 GPU_CFGS = ["cfg1_brachistochrone20", "cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40",
             "cfg5_lowthrust128", "ex05_goddard_knot25x2", "ex09_polar_tsto20x2", "ex10_lowthrust100",
-            "edge_table_lookup", "edge_stress_mixed", "edge_all_ops", "edge_nonautonomous"]
+            "edge_table_lookup", "edge_stress_mixed", "edge_all_ops", "edge_nonautonomous", "edge_picked_dynamics"]
 
 
 @pytest.mark.gpu

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 CFGS = ["cfg1_brachistochrone20", "cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40",
         "cfg5_lowthrust128", "ex05_goddard_knot25x2", "ex09_polar_tsto20x2", "ex10_lowthrust100",
-        "edge_table_lookup", "edge_stress_mixed", "edge_all_ops", "edge_nonautonomous", "edge_nonautonomous_big"]
+        "edge_table_lookup", "edge_stress_mixed", "edge_all_ops", "edge_nonautonomous", "edge_nonautonomous_big", "edge_picked_dynamics"]
 
 
 @pytest.fixture(scope="module")
