@@ -200,10 +200,30 @@ def test_numpy_idioms_trace_and_match(api, name):
         assert_J_close(J[b].T, J_ref, dust=1e-6)
 
 
-def test_node_reductions_inside_dynamics_are_rejected(api):
-    """A reduction over the nodes inside `dynamics` is not node-local: the tracer says so instead of
-    producing a dense Jacobian block the kernels do not model."""
-    from opengoddard_b200 import trace
-    pa = _small_problem(api, lambda x, y, u: y + np.sum(x), lambda x, y: 0.0)
-    with pytest.raises(trace.TraceError):
-        tape.build_ir(pa, None)
+def test_node_reductions_inside_dynamics_become_dense_columns(api):
+    """A reduction over the nodes inside `dynamics` (here sum(x)) is not node-local.  Round 1 refused it; since
+    round 2 every element the reduction reads is a global input of the node program and the Jacobian columns of
+    those variables are dense in the phase -- checked against the oracle (FD) and against complex-step
+    differentiation (exact mode)."""
+    from tests.test_exact import check_exact
+    f, g = (lambda x, y, u: y + np.sum(x) * 0.1 + 0.2 * np.max(u)), (lambda x, y: 0.0)
+    pa, po = _small_problem(api, f, g), _small_problem(og_numpy, f, g)
+    ir = tape.build_ir(pa, None)
+    assert len(ir.node_tapes[0].globals) == 12               # the 6 x's and the 6 u's
+    lb, ub = og_numpy.bounds_arrays(po)
+    emu = EmuProblem(ir, lb, ub)
+    P = np.asarray(po.p)[None] * (1.0 + 0.03 * np.random.default_rng(2).standard_normal((2, len(po.p))))
+    c, J = emu.eval_fd(P)
+    for b in range(2):
+        c_ref, J_ref = og_numpy.eval_fd(po, None, P[b], lb, ub)
+        assert_c_close(c[b], c_ref, J_ref, P[b])
+        assert_J_close(J[b].T, J_ref, dust=1e-6)
+    class W:                                                 # (check_exact wants a workload-like holder)
+        prob, obj = po, None
+    ce, Je = emu.eval_exact(P[0])
+    assert np.array_equal(ce[0], c[0])
+    x = np.clip(P[0], lb, ub)
+    x[12:18] += np.linspace(0.0, 0.05, 6)                    # (make max(u) unique: the arg-max is then differentiable)
+    ce, Je = emu.eval_exact(x)
+    cf, Jf = emu.eval_fd(x)
+    check_exact(Je[0].T, W, x, lb, ub, Jf[0].T)
