@@ -36,8 +36,9 @@ extern "C" {
  * A *node program* runs once per LGL node: OGB_LDP reads block `a` (state or control
  * number within the phase) of the decision vector at that node; operands beyond the phase's
  * blocks address first the program's per-node constant vectors (nodec_h: e.g. prob.time[s],
- * reference optimize.py:786-791), then its global variables (globals_h: final times read at
- * every node, optimize.py:349-360 -- non-autonomous dynamics).  The *scalar
+ * reference optimize.py:786-791), then its global variables (globals_h: single decision
+ * variables read at every node -- final times, optimize.py:349-360, non-autonomous dynamics; picked state /
+ * control elements such as x[0] or the operands of sum(x) inside `dynamics`).  The *scalar
  * program* runs once per decision vector: OGB_LDP reads variable `a` of p.          */
 enum ogb_opcode {
     OGB_NOP = 0,
@@ -97,7 +98,7 @@ typedef struct ogb_program {
     const ogb_out*  outs_h;   int32_t nouts;   /* slot i of OGB_OUT <-> outs_h[i] */
     int32_t nreg;
     const double*   nodec_h;  int32_t n_nodec; /* node programs: n_nodec vectors of `nodes` doubles (operand nb + i) */
-    const int32_t*  globals_h; int32_t nglobals; /* node programs: final-time variable indices (operand nb + n_nodec + i);
+    const int32_t*  globals_h; int32_t nglobals; /* node programs: decision-variable indices (operand nb + n_nodec + i);      
                                                   the Jacobian columns of these variables are dense in the phase  */
 } ogb_program;
 
