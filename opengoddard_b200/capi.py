@@ -227,6 +227,20 @@ def ogb():
         L.ogb_host_session_stats.argtypes = [vp, C.POINTER(OgbHostStats)]
         L.ogb_host_expand.restype = C.c_int
         L.ogb_host_expand.argtypes = [vp, vp, i32, C.c_size_t, i32, vp, i32, i32]
+        L.ogb_sqp_create.restype = C.c_void_p
+        L.ogb_sqp_create.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, C.c_double, i32, i32]
+        L.ogb_sqp_destroy.restype = None
+        L.ogb_sqp_destroy.argtypes = [vp]
+        L.ogb_sqp_bytes.restype = C.c_size_t
+        L.ogb_sqp_bytes.argtypes = [vp]
+        L.ogb_sqp_start.restype = C.c_int
+        L.ogb_sqp_start.argtypes = [vp, i32, vp]
+        L.ogb_sqp_step.restype = C.c_int
+        L.ogb_sqp_step.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+        L.ogb_sqp_scalars.restype = C.c_int
+        L.ogb_sqp_scalars.argtypes = [vp, i32, vp, vp]
+        L.ogb_sqp_launches.restype = C.c_longlong
+        L.ogb_sqp_launches.argtypes = [vp]
         _ogb = b
     return _ogb
 

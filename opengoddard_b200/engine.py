@@ -321,6 +321,10 @@ class DeviceProblem:
         self.tuned_threads = choice
         return timings
 
+    def device_sqp(self, max_batch, ftol=1e-6, maxiter=25):
+        """The batched SLSQP on the device (ogb_sqp_*): see DeviceSqp."""
+        return DeviceSqp(self, max_batch, ftol, maxiter)
+
     def host_session(self, max_batch, chunk=0, threads=0, exact=False):
         """Host-buffer entry point (ogb_host_eval_fd): numpy / pinned host arrays in and out."""
         return HostSession(self, max_batch, chunk, threads, exact)
@@ -563,3 +567,138 @@ def lgl_device(N, device="cuda:0"):
     if rc != 0:
         raise capi.OgbError("ogb_lgl_build failed: " + b.error())
     return tau, w, D
+
+
+SQP_SCALARS = ("f", "f0", "gs", "h1", "h2", "h3", "h4", "t", "t0", "alpha", "mode", "iter", "reset", "line",
+               "inconsistent", "nfev", "njev", "_17", "clk_build", "clk_lsei", "clk_lsi", "clk_nnls", "clk_finish", "clk_bfgs")
+
+
+class SqpKernel:
+    """Raw handle of the device SLSQP step (ogb_sqp_create / start / step / scalars) for one problem shape:
+    n variables, m constraints (the first meq equalities), the packed Jacobian pattern by variable
+    (colptr (n + 1), prow (nnz), rows in [0, m]; row m is the cost gradient) and the bounds."""
+
+    def __init__(self, b, torch, device, n, m, meq, colptr, prow, lb, ub, ftol, maxiter, max_batch):
+        self.b, self.torch, self.device = b, torch, device
+        self.n, self.m, self.meq, self.max_batch, self.maxiter = int(n), int(m), int(meq), int(max_batch), int(maxiter)
+        colptr = np.ascontiguousarray(colptr, dtype=np.int32)
+        prow = np.ascontiguousarray(prow, dtype=np.int32)
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        self.nnz = len(prow)
+        with torch.cuda.device(device):
+            self.h = b.lib.ogb_sqp_create(self.n, self.m, self.meq, self.nnz, colptr.ctypes.data, prow.ctypes.data,
+                                          lb.ctypes.data, ub.ctypes.data, float(ftol), self.maxiter, self.max_batch)
+        if not self.h:
+            raise capi.OgbError("ogb_sqp_create failed: " + b.error())
+
+    def _rc(self, rc, what):
+        if rc != 0:
+            raise capi.OgbError("%s failed: %s" % (what, self.b.error()))
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def bytes(self):
+        return int(self.b.lib.ogb_sqp_bytes(self.h))
+
+    @property
+    def launches(self):
+        return int(self.b.lib.ogb_sqp_launches(self.h))
+
+    def start(self, B):
+        with self.torch.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_sqp_start(self.h, int(B), self._stream()), "ogb_sqp_start")
+
+    def step(self, X, c, vals, mode):
+        """X (B, n) device in / out; c (B, m + 1), vals (B, nnz) device; mode (B,) int32 host array out."""
+        t = self.torch
+        B = X.shape[0]
+        assert X.is_contiguous() and c.is_contiguous() and vals.is_contiguous() and X.dtype == t.float64
+        assert tuple(c.shape) == (B, self.m + 1) and tuple(vals.shape) == (B, self.nnz) and mode.dtype == np.int32
+        with t.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_sqp_step(self.h, X.data_ptr(), c.data_ptr(), vals.data_ptr(), B, mode.ctypes.data,
+                                             self._stream()), "ogb_sqp_step")
+
+    def scalars(self, B):
+        sc = np.empty((B, 24), dtype=np.float64)
+        with self.torch.cuda.device(self.device):
+            self._rc(self.b.lib.ogb_sqp_scalars(self.h, int(B), sc.ctypes.data, self._stream()), "ogb_sqp_scalars")
+        return {name: sc[:, i] for i, name in enumerate(SQP_SCALARS)}
+
+    def close(self):
+        if getattr(self, "h", None):
+            with self.torch.cuda.device(self.device):
+                self.b.lib.ogb_sqp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceSqp:
+    """B independent SLSQP runs advanced in lock step entirely on the GPU (SURVEY.md section 8f row 1,
+    "device-side batched QP"): every round is one packed sweep (ogb_eval_sparse / ogb_eval_exact: c and the
+    Jacobian of every instance at its current x) and one ogb_sqp_step launch in which a thread block per
+    instance runs Kraft's SLSQP step -- BFGS update, the QP by LSQ/LSEI/LSI/LDP/NNLS, line search, convergence
+    tests (csrc/ogb_sqp.h) -- on those device buffers; only one int per instance returns to the host.
+    Opt-in: the default `solve_batch` keeps SciPy's compiled core per instance (bitwise SciPy)."""
+
+    def __init__(self, eng, max_batch, ftol=1e-6, maxiter=25):
+        self.eng, self.torch = eng, eng.torch
+        M, n = eng.nrows, eng.nvars
+        lin = eng.jac_pattern().astype(np.int64)
+        colptr = np.searchsorted(lin, np.arange(n + 1, dtype=np.int64) * M)
+        self.k = SqpKernel(eng.b, eng.torch, eng.device, n, M - 1, eng.meq, colptr, lin % M, eng.lb.cpu().numpy(),
+                           eng.ub.cpu().numpy(), ftol, maxiter, max_batch)
+        self.max_batch, self.maxiter = int(max_batch), int(maxiter)
+
+    @property
+    def bytes(self):
+        return self.k.bytes
+
+    @property
+    def launches(self):
+        return self.k.launches
+
+    def solve(self, X0, exact=False, max_rounds=None, callback=None):
+        """Run every row of X0 (B, nvars; host or device) to SLSQP's exit.  Returns dict(x (B, n) numpy, fun,
+        status, nit, nfev, njev, rounds)."""
+        t, eng = self.torch, self.eng
+        X = eng._check_P(X0).clone()
+        B = X.shape[0]
+        assert 0 < B <= self.max_batch
+        X = t.minimum(t.maximum(X, eng.lb), eng.ub).contiguous()     # scipy/optimize/_slsqp_py.py:322
+        c = t.empty((B, eng.nrows), dtype=t.float64, device=eng.device)
+        vals = t.empty((B, eng.nnz), dtype=t.float64, device=eng.device)
+        mode = np.zeros(B, dtype=np.int32)
+        evaluate = eng.eval_exact if exact else eng.eval_sparse
+        rounds = 0
+        # every SLSQP iteration is one gradient round and at least one line-search round (at most 11)
+        cap = max_rounds or (self.maxiter + 6) * 13
+        self.k.start(B)
+        while True:
+            evaluate(X, out_c=c, out_vals=vals)
+            self.k.step(X, c, vals, mode)
+            rounds += 1
+            if callback is not None:
+                callback(rounds, mode)
+            if not (np.abs(mode) == 1).any() or rounds >= cap:
+                break
+        sc = self.k.scalars(B)
+        fun = c[:, eng.nrows - 1].cpu().numpy()                  # (c holds the values at the final x of every instance)
+        return {"x": X.cpu().numpy(), "fun": fun, "status": sc["mode"].astype(int), "nit": sc["iter"].astype(int),
+                "nfev": sc["nfev"].astype(int), "njev": sc["njev"].astype(int), "rounds": rounds}
+
+    def close(self):
+        self.k.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

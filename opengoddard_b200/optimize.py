@@ -441,7 +441,7 @@ class Problem:
         return self._engine_for(obj).trajectories(P)
 
     def solve_batch(self, P0, obj, ftol=1e-6, maxiter=25, max_outer=None, threads=1, group=None, processes=0,
-                    jacobian="fd"):
+                    jacobian="fd", qp="scipy"):
         """Multi-start: solve the NLP from every row of P0 (B, nvars) at once.
 
         Under an initialised torch.distributed process group (one rank per GPU) the rows of P0
@@ -457,17 +457,26 @@ class Problem:
         worker processes (SciPy's step holds the GIL, so this is what makes the host side scale with
         the cores; sqp._ProcessStepper); a sqp.WorkerPool instance is used as is and left running, so
         repeated calls do not pay for starting the workers.  jacobian="exact": SLSQP is given the exact Jacobians (opt-in; the
-        reference's are forward differences).  Returns dict(x, fun, status, nit, outer)."""
+        reference's are forward differences).  qp="device" (opt-in): the whole SLSQP iteration -- BFGS update, the
+        QP, line search, convergence tests -- runs on the GPU too, one thread block per instance
+        (engine.DeviceSqp, csrc/ogb_sqp.h: Kraft's SLSQP restated, not SciPy's compiled core; identical iterates on
+        well-conditioned problems, same algorithm but not bitwise SciPy on ill-conditioned ones).
+        Returns dict(x, fun, status, nit, outer)."""
         from . import batch, sqp
         self._check_callbacks()
+        if qp not in ("scipy", "device"):
+            raise ValueError("qp must be 'scipy' or 'device'")
+        if qp == "device" and self.cost_derivative is not None:
+            raise NotImplementedError("qp='device' differentiates the cost on the device; cost_derivative is not used")
         eng = self._engine_for(obj)
         P0 = np.array(np.atleast_2d(P0), dtype=np.float64)
         return batch.run_sharded(
             lambda rows: self._solve_rows(eng, rows, obj, ftol, maxiter, max_outer, threads, sqp, processes,
-                                          exact=(jacobian == "exact")),
+                                          exact=(jacobian == "exact"), device_qp=(qp == "device")),
             P0, group=group, device=eng.device)
 
-    def _solve_rows(self, eng, P0, obj, ftol, maxiter, max_outer, threads, sqp, processes=0, exact=False):
+    def _solve_rows(self, eng, P0, obj, ftol, maxiter, max_outer, threads, sqp, processes=0, exact=False,
+                    device_qp=False):
         lb, ub = self.bounds_arrays()
         X = np.array(np.atleast_2d(P0), dtype=np.float64).reshape(-1, self.number_of_variables)
         B = X.shape[0]
@@ -476,6 +485,19 @@ class Problem:
         nit = np.zeros(B, dtype=int)
         outer = np.zeros(B, dtype=int)
         if B == 0:                                          # an empty shard (fewer starts than ranks)
+            return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
+        if device_qp:
+            with eng.device_sqp(B, ftol, maxiter) as dq:
+                for _ in range(self.maxIterator if max_outer is None else max_outer):
+                    ids = np.nonzero(status != 0)[0]
+                    if ids.size == 0:
+                        break
+                    res = dq.solve(X[ids], exact=exact)
+                    X[ids] = res["x"]
+                    status[ids] = res["status"]
+                    fun[ids] = res["fun"]
+                    nit[ids] += res["nit"]
+                    outer[ids] += 1
             return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
         grad = None
         if self.cost_derivative is not None:
@@ -552,6 +574,19 @@ class Problem:
         """SciPy-facing closures whose values AND Jacobians come from the CUDA kernels."""
         from . import engine
         eng = self._engine_for(obj, jit=False)   # one instance per call: latency-bound, skip NVRTC
+        if device_qp:
+            with eng.device_sqp(B, ftol, maxiter) as dq:
+                for _ in range(self.maxIterator if max_outer is None else max_outer):
+                    ids = np.nonzero(status != 0)[0]
+                    if ids.size == 0:
+                        break
+                    res = dq.solve(X[ids], exact=exact)
+                    X[ids] = res["x"]
+                    status[ids] = res["status"]
+                    fun[ids] = res["fun"]
+                    nit[ids] += res["nit"]
+                    outer[ids] += 1
+            return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
         grad = None
         if self.cost_derivative is not None:
             def grad(x):                                  # user gradient, host (reference :733)

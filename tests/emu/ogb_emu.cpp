@@ -155,3 +155,67 @@ int emu_eval_exact(void* h, const double* p, const double* lb, const double* ub,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- device SQP, serial group (csrc/ogb_sqp.h)
+#include "../../opengoddard_b200/csrc/ogb_sqp_host.h"
+
+struct EmuSqp {
+    OgsHostTables T;
+    int B = 0;
+    std::vector<double> state, scratch;
+};
+
+extern "C" {
+
+void* emu_sqp_create(int n, int m, int meq, int nnz, const int* colptr, const int* prow, const double* xl,
+                     const double* xu, double acc, int itermax, int B) {
+    EmuSqp* E = new EmuSqp();
+    if (!ogs_build_tables(n, m, meq, nnz, colptr, prow, xl, xu, acc, itermax, E->T, &g_err)) { delete E; return nullptr; }
+    OgsShape& S = E->T.S;
+    S.colptr = E->T.colptr.data(); S.prow = E->T.prow.data(); S.rowptr = E->T.rowptr.data();
+    S.rcol = E->T.rcol.data(); S.rpos = E->T.rpos.data(); S.blo = E->T.blo.data(); S.bhi = E->T.bhi.data();
+    S.xl = E->T.xl.data(); S.xu = E->T.xu.data();
+    E->B = B;
+    E->state.assign((size_t)B * S.state_doubles, 0.0);
+    for (int b = 0; b < B; ++b) E->state[(size_t)b * S.state_doubles + S.o_sc + OGS_MODE] = OGS_MODE_START;
+    E->scratch.assign(S.scratch_doubles, 0.0);
+    return E;
+}
+
+void emu_sqp_destroy(void* h) { delete (EmuSqp*)h; }
+
+// offsets (in doubles) of the persistent state: x0, s, g, mu, r, v, u, w, lt, dg, sc, total
+void emu_sqp_offsets(void* h, long long* out) {
+    const OgsShape& S = ((EmuSqp*)h)->T.S;
+    const size_t o[] = {S.o_x0, S.o_s, S.o_g, S.o_mu, S.o_r, S.o_v, S.o_u, S.o_w, S.o_lt, S.o_dg, S.o_sc, S.state_doubles};
+    for (int i = 0; i < 12; ++i) out[i] = (long long)o[i];
+}
+
+double* emu_sqp_state(void* h, int b) {
+    EmuSqp* E = (EmuSqp*)h;
+    return E->state.data() + (size_t)b * E->T.S.state_doubles;
+}
+
+// one reverse-communication step of every instance (x in / out)
+int emu_sqp_step(void* h, double* x, const double* c, const double* vals) {
+    EmuSqp* E = (EmuSqp*)h;
+    const OgsShape& S = E->T.S;
+    for (int b = 0; b < E->B; ++b) {
+        OgsSerial cx;
+        OgsInst I{&S, x + (size_t)b * S.n, c + (size_t)b * S.M, vals + (size_t)b * S.nnz,
+                  E->state.data() + (size_t)b * S.state_doubles, E->scratch.data()};
+        ogs_step(cx, I);
+    }
+    return 0;
+}
+
+// the QP alone on the state of instance b (LT, DG, g as stored): returns the mode; s and r are in the state
+int emu_sqp_lsq(void* h, int b, double* x, const double* c, const double* vals, int aug, double rho) {
+    EmuSqp* E = (EmuSqp*)h;
+    const OgsShape& S = E->T.S;
+    OgsSerial cx;
+    OgsInst I{&S, x, c, vals, E->state.data() + (size_t)b * S.state_doubles, E->scratch.data()};
+    return ogs_lsq(cx, I, aug != 0, rho);
+}
+
+}  // extern "C"
