@@ -84,15 +84,27 @@ struct OgsBlock {
         i = bi;
     }
     __device__ __forceinline__ long long clock() { return clock64(); }
+    double* wb;                         // dynamic shared memory: `wrows` row buffers per warp
+    int wstride, wrows;
+    __device__ __forceinline__ double* wbuf() { return wb + (size_t)warp * wrows * wstride; }
+    __device__ __forceinline__ void wsync() { __syncwarp(); }
+    __device__ __forceinline__ double wmax(double v) {
+        for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
 };
 
 __global__ void __launch_bounds__(OGS_THREADS)
 ogb_sqp_step_kernel(OgsShape S, double* X, const double* C, const double* vals, double* state, double* scratch, int B,
-                    int* ticket, int* mode_out) {
+                    int* ticket, int* mode_out, int wrows) {
+    extern __shared__ double s_rows[];
     __shared__ double red[32];
     __shared__ int redi[32];
     __shared__ int s_item;
     OgsBlock cx;
+    cx.wb = s_rows;
+    cx.wstride = (S.n1 + 3) & ~3;
+    cx.wrows = wrows;
     cx.tid = threadIdx.x; cx.nthr = blockDim.x; cx.warp = threadIdx.x >> 5; cx.nwarps = blockDim.x >> 5;
     cx.lane = threadIdx.x & 31; cx.wsize = 32; cx.red = red; cx.redi = redi;
     double* W = scratch + (size_t)blockIdx.x * S.scratch_doubles;
@@ -124,6 +136,8 @@ struct OgbDeviceSqp {
         *blo_d = nullptr, *bhi_d = nullptr, *ticket_d = nullptr, *mode_d = nullptr;
     double *xl_d = nullptr, *xu_d = nullptr, *state_d = nullptr, *scratch_d = nullptr;
     long long launches = 0;
+    size_t smem = 0;
+    int wrows = 1;
 };
 
 template <class T>
@@ -171,7 +185,17 @@ void* ogb_sqp_create(int nvars, int m, int meq, int nnz, const int32_t* colptr_h
             const int v = atoi(ev);
             if (v >= 32 && v <= OGS_THREADS && v % 32 == 0) q->threads = v;
         }
-        ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ogb_sqp_step_kernel, q->threads, 0) == cudaSuccess;
+        // rows a warp takes through the reflections at once (4, 2 or 1): as many as fit in ~96 KB per block
+        const size_t per_row = (size_t)(q->threads / 32) * ((S.n1 + 3) & ~3) * sizeof(double);
+        q->wrows = per_row * 4 <= 96 * 1024 ? 4 : (per_row * 2 <= 96 * 1024 ? 2 : 1);
+        if (const char* ev = getenv("OGB200_SQP_WROWS")) {
+            const int v = atoi(ev);
+            if (v == 1 || v == 2 || v == 4) q->wrows = v;
+        }
+        q->smem = per_row * q->wrows;
+        ok = q->smem <= 200 * 1024 &&
+             cudaFuncSetAttribute(ogb_sqp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem) == cudaSuccess &&
+             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ogb_sqp_step_kernel, q->threads, q->smem) == cudaSuccess;
         q->blocks = std::max(1, std::min(max_batch, q->sm_count * std::max(1, per_sm)));
     }
     ok = ok && upload(&q->colptr_d, q->T.colptr) == cudaSuccess && upload(&q->prow_d, q->T.prow) == cudaSuccess &&
@@ -223,8 +247,8 @@ int ogb_sqp_step(void* h, double* x, const double* c, const double* vals, int B,
     cudaStream_t st = (cudaStream_t)stream;
     OGS_CUDA(cudaMemsetAsync(q->ticket_d, 0, sizeof(int), st));
     const int blocks = std::min(q->blocks, B);
-    ogb_sqp_step_kernel<<<blocks, q->threads, 0, st>>>(q->T.S, x, c, vals, q->state_d, q->scratch_d, B, q->ticket_d,
-                                                        q->mode_d);
+    ogb_sqp_step_kernel<<<blocks, q->threads, q->smem, st>>>(q->T.S, x, c, vals, q->state_d, q->scratch_d, B, q->ticket_d,
+                                                        q->mode_d, q->wrows);
     OGS_CUDA(cudaGetLastError());
     q->launches += 1;
     if (mode_h) {

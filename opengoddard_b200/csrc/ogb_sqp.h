@@ -57,7 +57,7 @@ struct OgsShape {
     size_t o_x0, o_s, o_g, o_mu, o_r, o_v, o_u, o_w, o_lt, o_dg, o_sc, state_doubles;
     // per-block scratch, offsets in doubles
     size_t o_E, o_f, o_C, o_d, o_ups, o_G, o_h, o_xq, o_wq, o_E2T, o_GT, o_An, o_bn, o_zn, o_xn, o_wn, o_ucol,
-        o_f2, o_fres, o_idx, scratch_doubles;
+        o_f2, o_fres, o_binv, o_idx, scratch_doubles;
 };
 
 enum { OGS_F = 0, OGS_F0, OGS_GS, OGS_H1, OGS_H2, OGS_H3, OGS_H4, OGS_T, OGS_T0, OGS_ALPHA, OGS_MODE, OGS_ITER,
@@ -86,7 +86,7 @@ static inline void ogs_layout(OgsShape& S) {
     S.o_ups = take(S.meq); S.o_G = take(mg * n1); S.o_h = take(mg); S.o_xq = take(n1); S.o_wq = take(S.meq + mg);
     S.o_E2T = take((size_t)S.lmax * n1); S.o_GT = take(l1 * mg); S.o_An = take(l1 * mg); S.o_bn = take(l1);
     S.o_zn = take(l1); S.o_xn = take(mg); S.o_wn = take(mg); S.o_ucol = take(l1);
-    S.o_f2 = take(n1); S.o_fres = take(n1);
+    S.o_f2 = take(n1); S.o_fres = take(n1); S.o_binv = take(S.meq);
     S.o_idx = take((mg + 1) / 2 + 1);
     S.scratch_doubles = o;
 }
@@ -100,6 +100,11 @@ struct OgsSerial {
     OGS_HD double wsum(double v) { return v; }
     OGS_HD void argbest(double& v, int& i, bool) {}
     OGS_HD long long clock() { return 0; }
+    double* wb = nullptr;              // one row buffer (n + 1 doubles) per warp
+    int wrows = 1, wstride = 0;        // rows a warp keeps in its buffer at once, doubles per row
+    OGS_HD double* wbuf() { return wb; }
+    OGS_HD void wsync() {}
+    OGS_HD double wmax(double v) { return v; }
 };
 
 // ---------------------------------------------------------------- Householder (Lawson & Hanson H12)
@@ -170,6 +175,62 @@ OGS_FN void ogs_h12_vec(Cx& cx, const double* u, size_t st, int p, int l1, int l
         for (int k = l1 + cx.tid; k < len; k += cx.nthr) c[k] += sm * u[k * st];
     }
     cx.sync();
+}
+
+// apply the reflection defined by u (pivot p, zeroing p + 1 .. len; binv = 1 / (up u[p]), 0 = identity) to R rows
+// at once: rows[r] = base + r * stride (a warp's buffer in shared memory, or rows of a matrix in global memory).
+// The R dot products and updates are independent, so their loads and shuffles overlap.
+template <int R, class Cx>
+OGS_FN void ogs_reflect_rows(Cx& cx, double* base, size_t stride, const double* u, int p, int len, double up, double binv) {
+    if (binv == 0.0) return;
+    double sm[R], rp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) sm[r] = 0.0;
+    for (int k = p + 1 + cx.lane; k < len; k += cx.wsize) {
+        const double uk = u[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) sm[r] += base[r * stride + k] * uk;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rp[r] = base[r * stride + p];
+#pragma unroll
+    for (int r = 0; r < R; ++r) sm[r] = cx.wsum(sm[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        sm[r] += rp[r] * up;
+        if (sm[r] != 0.0) {
+            sm[r] *= binv;
+            if (cx.lane == 0) base[r * stride + p] = rp[r] + sm[r] * up;
+        }
+    }
+    for (int k = p + 1 + cx.lane; k < len; k += cx.wsize) {
+        const double uk = u[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (sm[r] != 0.0) base[r * stride + k] += sm[r] * uk;
+    }
+    cx.wsync();
+}
+
+// the rows [0, nrows) of a matrix in global memory (leading dimension ldc) through ONE reflection, 4 rows per warp at once
+template <class Cx>
+OGS_FN void ogs_reflect_matrix(Cx& cx, double* Cm, size_t ldc, int nrows, const double* u, int p, int len, double up, double binv) {
+    if (binv == 0.0 || nrows <= 0) return;
+    for (int r0 = cx.warp * 4; r0 < nrows; r0 += cx.nwarps * 4) {
+        double* base = Cm + (size_t)r0 * ldc;
+        const int cnt = nrows - r0;
+        if (cnt >= 4) ogs_reflect_rows<4>(cx, base, ldc, u, p, len, up, binv);
+        else if (cnt == 3) ogs_reflect_rows<3>(cx, base, ldc, u, p, len, up, binv);
+        else if (cnt == 2) ogs_reflect_rows<2>(cx, base, ldc, u, p, len, up, binv);
+        else ogs_reflect_rows<1>(cx, base, ldc, u, p, len, up, binv);
+    }
+}
+
+// `cnt` (<= wrows) rows of a warp's buffer through the reflections p0 .. p1 - 1 defined by the rows of C
+template <int R, class Cx>
+OGS_FN void ogs_reflect_buffer(Cx& cx, double* rb, size_t stride, const double* C, size_t ld, const double* ups,
+                               const double* binv, int p0, int p1, int len) {
+    for (int p = p0; p < p1; ++p) ogs_reflect_rows<R>(cx, rb, stride, C + (size_t)p * ld, p, len, ups[p], binv[p]);
 }
 
 // ---------------------------------------------------------------- NNLS (Lawson & Hanson, chapter 23)
@@ -371,7 +432,7 @@ OGS_FN int ogs_nnls(Cx& cx, double* A, size_t lda, int mrows, int ncol, double* 
 // Work arrays of one QP (views into the block's scratch)
 struct OgsQp {
     int nq, mc, mg, ld;                // variables, equality rows, inequality rows (with bounds), leading dim
-    double *E, *f, *C, *d, *ups, *G, *h, *x, *w, *E2T, *GT, *An, *bn, *zn, *xn, *wn, *ucol, *f2, *fres;
+    double *E, *f, *C, *d, *ups, *binv, *G, *h, *x, *w, *E2T, *GT, *An, *bn, *zn, *xn, *wn, *ucol, *f2, *fres;
     int* idx;
     size_t ldg;                        // leading dimension of GT / An ( = mg of the shape)
     double* clk;                       // the instance's scalars (cycle counters)
@@ -384,15 +445,65 @@ OGS_FN int ogs_lsei(Cx& cx, OgsQp& Q) {
     if (mc >= nq || mg <= 0) return 2;
     const int l = nq - mc;
     long long t0c = cx.clock();
-    // ---- triangularise C from the right, apply to E and G
+    // ---- triangularise C from the right (C K = [C1 0]) and apply K to E and G: every row goes through the same
+    //      reflections in the same order as in Lawson & Hanson's loop.
+    //      Phase 1: step i defines H_i from row i of C (one warp) and applies it to the rows below (all warps,
+    //      four rows per warp in flight).
     for (int i = 0; i < mc; ++i) {
-        bool ident;
         double* row = Q.C + (size_t)i * ld;
-        const double up = ogs_h12_construct(cx, row, 1, i, i + 1, nq, ident);
-        if (cx.tid == 0) Q.ups[i] = ident ? 0.0 : up;
-        ogs_h12_rows(cx, row, i, i + 1, nq, up, ident, Q.C + (size_t)(i + 1) * ld, ld, mc - i - 1);
-        ogs_h12_rows(cx, row, i, i + 1, nq, up, ident, Q.E, ld, me);
-        ogs_h12_rows(cx, row, i, i + 1, nq, up, ident, Q.G, ld, mg);
+        if (cx.warp == 0) {
+            double up = 0.0, binv = 0.0;
+            if (i + 1 < nq) {
+                double cl = 0.0;
+                for (int k = i + 1 + cx.lane; k < nq; k += cx.wsize) cl = fmax(cl, fabs(row[k]));
+                cl = cx.wmax(cl);
+                const double upiv = row[i];
+                cl = fmax(cl, fabs(upiv));
+                if (cl > 0.0) {
+                    const double clinv = 1.0 / cl;
+                    double sm = 0.0;
+                    for (int k = i + 1 + cx.lane; k < nq; k += cx.wsize) { const double t = row[k] * clinv; sm += t * t; }
+                    sm = cx.wsum(sm);
+                    sm += (upiv * clinv) * (upiv * clinv);
+                    cl = cl * sqrt(sm);
+                    if (upiv > 0.0) cl = -cl;
+                    up = upiv - cl;
+                    const double b = up * cl;
+                    if (b < 0.0) binv = 1.0 / b;
+                    cx.wsync();
+                    if (cx.lane == 0) row[i] = cl;
+                }
+            }
+            if (cx.lane == 0) { Q.ups[i] = up; Q.binv[i] = binv; }
+        }
+        cx.sync();
+        ogs_reflect_matrix(cx, Q.C + (size_t)(i + 1) * ld, ld, mc - i - 1, row, i, nq, Q.ups[i], Q.binv[i]);
+        cx.sync();
+    }
+    //      Phase 2: the rows of E and G are independent of each other: a warp keeps `wrows` of them in shared
+    //      memory and takes them through H_0 .. H_{mc-1} without a block barrier or a global round trip per step.
+    {
+        const int R = cx.wrows;
+        const size_t stride = cx.wstride;
+        double* rb = cx.wbuf();
+        for (int r0 = cx.warp * R; r0 < me + mg; r0 += cx.nwarps * R) {
+            const int cnt = (me + mg - r0) < R ? (me + mg - r0) : R;
+            for (int r = 0; r < R; ++r) {
+                const int rr = r0 + r;
+                const double* src = rr < me ? Q.E + (size_t)rr * ld : Q.G + (size_t)(rr - me) * ld;
+                for (int k = cx.lane; k < nq; k += cx.wsize) rb[r * stride + k] = (r < cnt) ? src[k] : 0.0;
+            }
+            cx.wsync();
+            if (R == 4) ogs_reflect_buffer<4>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
+            else if (R == 2) ogs_reflect_buffer<2>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
+            else ogs_reflect_buffer<1>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
+            for (int r = 0; r < cnt; ++r) {
+                const int rr = r0 + r;
+                double* dst = rr < me ? Q.E + (size_t)rr * ld : Q.G + (size_t)(rr - me) * ld;
+                for (int k = cx.lane; k < nq; k += cx.wsize) dst[k] = rb[r * stride + k];
+            }
+            cx.wsync();
+        }
     }
     cx.sync();
     if (cx.tid == 0) Q.clk[OGS_CLK_LSEI] += (double)(cx.clock() - t0c);
@@ -583,7 +694,7 @@ OGS_FN int ogs_lsq(Cx& cx, const OgsInst& I, bool aug, double rho) {
     Q.E = W + S.o_E; Q.f = W + S.o_f; Q.C = W + S.o_C; Q.d = W + S.o_d; Q.ups = W + S.o_ups; Q.G = W + S.o_G;
     Q.h = W + S.o_h; Q.x = W + S.o_xq; Q.w = W + S.o_wq; Q.E2T = W + S.o_E2T; Q.GT = W + S.o_GT; Q.An = W + S.o_An;
     Q.bn = W + S.o_bn; Q.zn = W + S.o_zn; Q.xn = W + S.o_xn; Q.wn = W + S.o_wn; Q.ucol = W + S.o_ucol;
-    Q.f2 = W + S.o_f2; Q.fres = W + S.o_fres; Q.idx = (int*)(W + S.o_idx);
+    Q.f2 = W + S.o_f2; Q.fres = W + S.o_fres; Q.binv = W + S.o_binv; Q.idx = (int*)(W + S.o_idx);
     Q.clk = st + S.o_sc;
     long long t0c = cx.clock();
     // ---- E = D^1/2 L' (upper triangular), f = -E^-T g

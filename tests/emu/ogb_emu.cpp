@@ -162,7 +162,7 @@ int emu_eval_exact(void* h, const double* p, const double* lb, const double* ub,
 struct EmuSqp {
     OgsHostTables T;
     int B = 0;
-    std::vector<double> state, scratch;
+    std::vector<double> state, scratch, rowbuf;
 };
 
 extern "C" {
@@ -179,6 +179,7 @@ void* emu_sqp_create(int n, int m, int meq, int nnz, const int* colptr, const in
     E->state.assign((size_t)B * S.state_doubles, 0.0);
     for (int b = 0; b < B; ++b) E->state[(size_t)b * S.state_doubles + S.o_sc + OGS_MODE] = OGS_MODE_START;
     E->scratch.assign(S.scratch_doubles, 0.0);
+    E->rowbuf.assign(S.n1, 0.0);
     return E;
 }
 
@@ -202,6 +203,7 @@ int emu_sqp_step(void* h, double* x, const double* c, const double* vals) {
     const OgsShape& S = E->T.S;
     for (int b = 0; b < E->B; ++b) {
         OgsSerial cx;
+        cx.wb = E->rowbuf.data(); cx.wrows = 1; cx.wstride = S.n1;
         OgsInst I{&S, x + (size_t)b * S.n, c + (size_t)b * S.M, vals + (size_t)b * S.nnz,
                   E->state.data() + (size_t)b * S.state_doubles, E->scratch.data()};
         ogs_step(cx, I);
@@ -214,6 +216,7 @@ int emu_sqp_lsq(void* h, int b, double* x, const double* c, const double* vals, 
     EmuSqp* E = (EmuSqp*)h;
     const OgsShape& S = E->T.S;
     OgsSerial cx;
+    cx.wb = E->rowbuf.data(); cx.wrows = 1; cx.wstride = S.n1;
     OgsInst I{&S, x, c, vals, E->state.data() + (size_t)b * S.state_doubles, E->scratch.data()};
     return ogs_lsq(cx, I, aug != 0, rho);
 }
