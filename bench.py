@@ -449,6 +449,32 @@ def extras(eng, wl, cfg, workloads, P, P_host, torch, args, api):
         out["solve_batch"]["reference"] = reference_solve_rate(cfg, iters)
     except Exception as ex:
         out["solve_error"] = str(ex)[:300]
+    # ---- the same multi-start with the whole SLSQP iteration on the device (opt-in, qp="device"): the packed sweep
+    #      and one thread block per instance for the QP / line search / BFGS; only a mode word per instance returns
+    try:
+        import time as _t
+        Sd = max(1, min(B, 4 * max(1, int(args.solve_starts))))
+        iters = 6
+        X0 = P_host[:Sd].numpy().copy()
+        with eng.device_sqp(Sd, 1e-10, iters) as dq:
+            dq.solve(X0[:min(Sd, 8)])
+            torch.cuda.synchronize()
+            t0 = _t.perf_counter()
+            res = dq.solve(X0)
+            torch.cuda.synchronize()
+            wall = _t.perf_counter() - t0
+            sc = dq.k.scalars(Sd)
+            clk = {k[4:]: float(sc[k].sum()) for k in sc if k.startswith("clk_")}
+            tot = sum(clk.values()) or 1.0
+            done = int(res["nit"].sum())
+            out["solve_batch_device_qp"] = {
+                "starts": Sd, "slsqp_iterations_each": iters, "instance_iterations_per_s": done / wall, "wall_s": wall,
+                "instance_iterations": done, "rounds": int(res["rounds"]), "device_bytes": dq.bytes,
+                "qp_phase_share": {k: round(v / tot, 3) for k, v in clk.items()},
+                "what": "Problem.solve_batch(qp='device'): Kraft's SLSQP restated as one thread block per instance "
+                        "(ogb_sqp_step) on the packed sweep's output; host wall clock, synchronised"}
+    except Exception as ex:
+        out["solve_device_error"] = str(ex)[:300]
     return out
 
 

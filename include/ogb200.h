@@ -366,6 +366,35 @@ int   ogb_host_eval_fd_scatter(void* session, const double* p_h, const double* l
 int ogb_host_expand(const double* vals_h, const uint32_t* lin_h, int nnz, size_t nM, int B,
                     double* J_h, int mode, int threads);
 
+/* ---- batched SLSQP on the device ("device-side batched QP") ------------------
+ * What scipy.optimize.minimize(method="SLSQP") runs per instance for the reference's Problem.solve
+ * (/root/reference/OpenGoddard/optimize.py:738-755; driver loop scipy/optimize/_slsqp_py.py:524-555), for B
+ * instances at once: one thread block advances one instance through one reverse-communication step of
+ * Kraft's SLSQP -- damped BFGS update of L D L', the QP as LSQ -> LSEI -> LSI -> LDP -> NNLS (augmented with the
+ * slack variable when the linearisation is inconsistent), the L1 merit line search, the convergence tests
+ * (csrc/ogb_sqp.h restates the published algorithm; SciPy's compiled core is not part of the reference tree).
+ * The caller alternates   ogb_eval_sparse / ogb_eval_exact (c, vals at x)   and   ogb_sqp_step   until no
+ * instance reports mode 1 or -1.  Opt-in: the default multi-start keeps SciPy's own core on the host.
+ *
+ * ogb_sqp_create: nvars, m constraints (the first meq are equalities; m >= 1, meq < nvars, at least one
+ * inequality or finite bound), the packed Jacobian pattern BY VARIABLE (colptr_h [nvars + 1], prow_h [nnz], rows
+ * in [0, m], row m = cost gradient: ogb_jac_pattern's ascending indices j * nrows + r, split), the bounds
+ * (xl_h / xu_h [nvars], +-inf or NaN = none), SLSQP's acc (ftol) and iteration limit, and the largest batch.
+ * ogb_sqp_start: (re)start B instances -- the next step treats c / vals as the values at the start points.
+ * ogb_sqp_step: x [B, nvars] device, in / out; c [B, m + 1], vals [B, nnz] device, as written by the sweep
+ * kernel at x; mode_h [B] host (may be NULL: no synchronisation): SLSQP's mode per instance after the step --
+ * 1: evaluate c at x (line search), -1: evaluate c and the Jacobian at x, 0: converged, 2..9: SLSQP's exit modes.
+ * ogb_sqp_scalars: [B, 24] doubles per instance to the host: f, f0, gs, h1, h2, h3, h4, t, t0, alpha, mode, iter,
+ * reset, line, inconsistent, nfev, njev, (unused), SM cycles spent in the QP phases (6).                        */
+void*  ogb_sqp_create(int nvars, int m, int meq, int nnz, const int32_t* colptr_h, const int32_t* prow_h,
+                      const double* xl_h, const double* xu_h, double acc, int maxiter, int max_batch);
+void   ogb_sqp_destroy(void* sqp);
+size_t ogb_sqp_bytes(void* sqp);
+int    ogb_sqp_start(void* sqp, int B, void* stream);
+int    ogb_sqp_step(void* sqp, double* x, const double* c, const double* vals, int B, int32_t* mode_h, void* stream);
+int    ogb_sqp_scalars(void* sqp, int B, double* sc_h, void* stream);
+long long ogb_sqp_launches(void* sqp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,7 +94,9 @@ struct OgsBlock {
     }
 };
 
-__global__ void __launch_bounds__(OGS_THREADS)
+// MINB: resident blocks per SM the register allocation aims at (2: no spills; 3, 4: more warps to hide latency)
+template <int MINB>
+__global__ void __launch_bounds__(OGS_THREADS, MINB)
 ogb_sqp_step_kernel(OgsShape S, double* X, const double* C, const double* vals, double* state, double* scratch, int B,
                     int* ticket, int* mode_out, int wrows) {
     extern __shared__ double s_rows[];
@@ -137,7 +139,8 @@ struct OgbDeviceSqp {
     double *xl_d = nullptr, *xu_d = nullptr, *state_d = nullptr, *scratch_d = nullptr;
     long long launches = 0;
     size_t smem = 0;
-    int wrows = 1;
+    int wrows = 1, minb = 2;
+    const void* fn = nullptr;
 };
 
 template <class T>
@@ -193,9 +196,15 @@ void* ogb_sqp_create(int nvars, int m, int meq, int nnz, const int32_t* colptr_h
             if (v == 1 || v == 2 || v == 4) q->wrows = v;
         }
         q->smem = per_row * q->wrows;
+        if (const char* ev = getenv("OGB200_SQP_MINBLOCKS")) {
+            const int v = atoi(ev);
+            if (v >= 2 && v <= 4) q->minb = v;
+        }
+        q->fn = q->minb == 4 ? (const void*)ogb_sqp_step_kernel<4>
+                             : (q->minb == 3 ? (const void*)ogb_sqp_step_kernel<3> : (const void*)ogb_sqp_step_kernel<2>);
         ok = q->smem <= 200 * 1024 &&
-             cudaFuncSetAttribute(ogb_sqp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem) == cudaSuccess &&
-             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ogb_sqp_step_kernel, q->threads, q->smem) == cudaSuccess;
+             cudaFuncSetAttribute(q->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem) == cudaSuccess &&
+             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q->fn, q->threads, q->smem) == cudaSuccess;
         q->blocks = std::max(1, std::min(max_batch, q->sm_count * std::max(1, per_sm)));
     }
     ok = ok && upload(&q->colptr_d, q->T.colptr) == cudaSuccess && upload(&q->prow_d, q->T.prow) == cudaSuccess &&
@@ -247,8 +256,13 @@ int ogb_sqp_step(void* h, double* x, const double* c, const double* vals, int B,
     cudaStream_t st = (cudaStream_t)stream;
     OGS_CUDA(cudaMemsetAsync(q->ticket_d, 0, sizeof(int), st));
     const int blocks = std::min(q->blocks, B);
-    ogb_sqp_step_kernel<<<blocks, q->threads, q->smem, st>>>(q->T.S, x, c, vals, q->state_d, q->scratch_d, B, q->ticket_d,
-                                                        q->mode_d, q->wrows);
+    {
+        OgsShape S = q->T.S;
+        double *state = q->state_d, *scratch = q->scratch_d;
+        int *ticket = q->ticket_d, *mode_d = q->mode_d, wrows = q->wrows, Bv = B;
+        void* kargs[] = {&S, &x, &c, &vals, &state, &scratch, &Bv, &ticket, &mode_d, &wrows};
+        OGS_CUDA(cudaLaunchKernel(q->fn, dim3((unsigned)blocks), dim3((unsigned)q->threads), kargs, q->smem, st));
+    }
     OGS_CUDA(cudaGetLastError());
     q->launches += 1;
     if (mode_h) {
