@@ -574,19 +574,6 @@ class Problem:
         """SciPy-facing closures whose values AND Jacobians come from the CUDA kernels."""
         from . import engine
         eng = self._engine_for(obj, jit=False)   # one instance per call: latency-bound, skip NVRTC
-        if device_qp:
-            with eng.device_sqp(B, ftol, maxiter) as dq:
-                for _ in range(self.maxIterator if max_outer is None else max_outer):
-                    ids = np.nonzero(status != 0)[0]
-                    if ids.size == 0:
-                        break
-                    res = dq.solve(X[ids], exact=exact)
-                    X[ids] = res["x"]
-                    status[ids] = res["status"]
-                    fun[ids] = res["fun"]
-                    nit[ids] += res["nit"]
-                    outer[ids] += 1
-            return {"x": X, "fun": fun, "status": status, "nit": nit, "outer": outer}
         grad = None
         if self.cost_derivative is not None:
             def grad(x):                                  # user gradient, host (reference :733)
