@@ -464,7 +464,7 @@ def extras(eng, wl, cfg, workloads, P, P_host, torch, args, api):
             torch.cuda.synchronize()
             wall = _t.perf_counter() - t0
             sc = dq.k.scalars(Sd)
-            clk = {k[4:]: float(sc[k].sum()) for k in sc if k.startswith("clk_")}
+            clk = {k[4:]: float(sc[k].sum()) for k in sc if k.startswith("clk_") and k != "clk_lsei_phase1"}
             tot = sum(clk.values()) or 1.0
             done = int(res["nit"].sum())
             out["solve_batch_device_qp"] = {

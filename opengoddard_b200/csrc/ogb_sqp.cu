@@ -84,8 +84,9 @@ struct OgsBlock {
         i = bi;
     }
     __device__ __forceinline__ long long clock() { return clock64(); }
+    static constexpr bool kLanes32 = true;
     double* wb;                         // dynamic shared memory: `wrows` row buffers per warp
-    int wstride, wrows;
+    int wstride, wrows, flags;
     __device__ __forceinline__ double* wbuf() { return wb + (size_t)warp * wrows * wstride; }
     __device__ __forceinline__ void wsync() { __syncwarp(); }
     __device__ __forceinline__ double wmax(double v) {
@@ -98,7 +99,7 @@ struct OgsBlock {
 template <int MINB>
 __global__ void __launch_bounds__(OGS_THREADS, MINB)
 ogb_sqp_step_kernel(OgsShape S, double* X, const double* C, const double* vals, double* state, double* scratch, int B,
-                    int* ticket, int* mode_out, int wrows) {
+                    int* ticket, int* mode_out, int wrows, int flags) {
     extern __shared__ double s_rows[];
     __shared__ double red[32];
     __shared__ int redi[32];
@@ -107,6 +108,7 @@ ogb_sqp_step_kernel(OgsShape S, double* X, const double* C, const double* vals, 
     cx.wb = s_rows;
     cx.wstride = (S.n1 + 3) & ~3;
     cx.wrows = wrows;
+    cx.flags = flags;
     cx.tid = threadIdx.x; cx.nthr = blockDim.x; cx.warp = threadIdx.x >> 5; cx.nwarps = blockDim.x >> 5;
     cx.lane = threadIdx.x & 31; cx.wsize = 32; cx.red = red; cx.redi = redi;
     double* W = scratch + (size_t)blockIdx.x * S.scratch_doubles;
@@ -139,7 +141,7 @@ struct OgbDeviceSqp {
     double *xl_d = nullptr, *xu_d = nullptr, *state_d = nullptr, *scratch_d = nullptr;
     long long launches = 0;
     size_t smem = 0;
-    int wrows = 1, minb = 2;
+    int wrows = 1, minb = 2, flags = 1;
     const void* fn = nullptr;
 };
 
@@ -196,6 +198,7 @@ void* ogb_sqp_create(int nvars, int m, int meq, int nnz, const int32_t* colptr_h
             if (v == 1 || v == 2 || v == 4) q->wrows = v;
         }
         q->smem = per_row * q->wrows;
+        if (const char* ev = getenv("OGB200_SQP_FLAGS")) q->flags = atoi(ev);   // bit 0: register-resident reflectors
         if (const char* ev = getenv("OGB200_SQP_MINBLOCKS")) {
             const int v = atoi(ev);
             if (v >= 2 && v <= 4) q->minb = v;
@@ -259,8 +262,8 @@ int ogb_sqp_step(void* h, double* x, const double* c, const double* vals, int B,
     {
         OgsShape S = q->T.S;
         double *state = q->state_d, *scratch = q->scratch_d;
-        int *ticket = q->ticket_d, *mode_d = q->mode_d, wrows = q->wrows, Bv = B;
-        void* kargs[] = {&S, &x, &c, &vals, &state, &scratch, &Bv, &ticket, &mode_d, &wrows};
+        int *ticket = q->ticket_d, *mode_d = q->mode_d, wrows = q->wrows, Bv = B, flags = q->flags;
+        void* kargs[] = {&S, &x, &c, &vals, &state, &scratch, &Bv, &ticket, &mode_d, &wrows, &flags};
         OGS_CUDA(cudaLaunchKernel(q->fn, dim3((unsigned)blocks), dim3((unsigned)q->threads), kargs, q->smem, st));
     }
     OGS_CUDA(cudaGetLastError());

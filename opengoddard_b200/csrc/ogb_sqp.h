@@ -32,6 +32,9 @@
 #define OGS_FN
 #endif
 
+// fused multiply-add in the hot loops of the QP (one FP64 pipe slot instead of two); this solver is pinned to the
+// restatement by tolerance, not bitwise, so contraction is allowed here (the sweep kernel stays -fmad=false)
+#define OGS_FMA(a, b, c) fma((a), (b), (c))
 #define OGS_EPS 2.220446049250313e-16
 #define OGS_ALFMIN 0.1
 #define OGS_INF (1.0 / 0.0)
@@ -105,6 +108,8 @@ struct OgsSerial {
     OGS_HD double* wbuf() { return wb; }
     OGS_HD void wsync() {}
     OGS_HD double wmax(double v) { return v; }
+    static constexpr bool kLanes32 = false;   // (the register-resident reflector path needs 32 lanes)
+    int flags = 0;
 };
 
 // ---------------------------------------------------------------- Householder (Lawson & Hanson H12)
@@ -144,14 +149,15 @@ OGS_FN void ogs_h12_rows(Cx& cx, const double* u, int p, int l1, int len, double
     for (int r = cx.warp; r < nrows; r += cx.nwarps) {
         double* row = Cm + (size_t)r * ldc;
         double sm = 0.0;
-        for (int k = l1 + cx.lane; k < len; k += cx.wsize) sm += row[k] * u[k];
+        for (int k = l1 + cx.lane; k < len; k += cx.wsize) sm = OGS_FMA(row[k], u[k], sm);
         const double rp = row[p];
         sm = cx.wsum(sm);
+        cx.wsync();
         sm += rp * up;
         if (sm != 0.0) {
             sm *= b;
             if (cx.lane == 0) row[p] = rp + sm * up;
-            for (int k = l1 + cx.lane; k < len; k += cx.wsize) row[k] += sm * u[k];
+            for (int k = l1 + cx.lane; k < len; k += cx.wsize) row[k] = OGS_FMA(sm, u[k], row[k]);
         }
     }
     cx.sync();
@@ -189,12 +195,13 @@ OGS_FN void ogs_reflect_rows(Cx& cx, double* base, size_t stride, const double* 
     for (int k = p + 1 + cx.lane; k < len; k += cx.wsize) {
         const double uk = u[k];
 #pragma unroll
-        for (int r = 0; r < R; ++r) sm[r] += base[r * stride + k] * uk;
+        for (int r = 0; r < R; ++r) sm[r] = OGS_FMA(base[r * stride + k], uk, sm[r]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) rp[r] = base[r * stride + p];
 #pragma unroll
     for (int r = 0; r < R; ++r) sm[r] = cx.wsum(sm[r]);
+    cx.wsync();                                   // (every lane has read its operands before any lane writes)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         sm[r] += rp[r] * up;
@@ -207,7 +214,7 @@ OGS_FN void ogs_reflect_rows(Cx& cx, double* base, size_t stride, const double* 
         const double uk = u[k];
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (sm[r] != 0.0) base[r * stride + k] += sm[r] * uk;
+            if (sm[r] != 0.0) base[r * stride + k] = OGS_FMA(sm[r], uk, base[r * stride + k]);
     }
     cx.wsync();
 }
@@ -231,6 +238,58 @@ template <int R, class Cx>
 OGS_FN void ogs_reflect_buffer(Cx& cx, double* rb, size_t stride, const double* C, size_t ld, const double* ups,
                                const double* binv, int p0, int p1, int len) {
     for (int p = p0; p < p1; ++p) ogs_reflect_rows<R>(cx, rb, stride, C + (size_t)p * ld, p, len, ups[p], binv[p]);
+}
+
+// The same for a 32-lane warp and at most 32 * NK columns: lane owns columns lane + 32 t.  The reflector of step
+// p + 1 (and its up / binv) is fetched into registers while step p is being applied, so the L2 latency of the
+// rows of C is hidden behind the arithmetic instead of being paid once per reflection.
+template <int R, int NK, class Cx>
+OGS_FN void ogs_reflect_buffer_reg(Cx& cx, double* rb, size_t stride, const double* C, size_t ld, const double* ups,
+                                   const double* binv, int p0, int p1, int len) {
+    if (p1 <= p0) return;
+    double un[NK], upn, bvn;
+    {
+        const double* u = C + (size_t)p0 * ld;
+#pragma unroll
+        for (int t = 0; t < NK; ++t) { const int k = cx.lane + 32 * t; un[t] = (k > p0 && k < len) ? u[k] : 0.0; }
+        upn = ups[p0]; bvn = binv[p0];
+    }
+    for (int p = p0; p < p1; ++p) {
+        double uc[NK];
+#pragma unroll
+        for (int t = 0; t < NK; ++t) uc[t] = un[t];
+        const double up = upn, bv = bvn;
+        if (p + 1 < p1) {
+            const double* u = C + (size_t)(p + 1) * ld;
+#pragma unroll
+            for (int t = 0; t < NK; ++t) { const int k = cx.lane + 32 * t; un[t] = (k > p + 1 && k < len) ? u[k] : 0.0; }
+            upn = ups[p + 1]; bvn = binv[p + 1];
+        }
+        if (bv == 0.0) continue;
+        double sm[R], rp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double a = 0.0;
+#pragma unroll
+            for (int t = 0; t < NK; ++t) { const int k = cx.lane + 32 * t; if (k < len) a = OGS_FMA(rb[r * stride + k], uc[t], a); }
+            sm[r] = a;
+            rp[r] = rb[r * stride + p];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) sm[r] = cx.wsum(sm[r]);
+        cx.wsync();                               // (every lane has read its operands before any lane writes)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            sm[r] += rp[r] * up;
+            if (sm[r] != 0.0) {
+                sm[r] *= bv;
+#pragma unroll
+                for (int t = 0; t < NK; ++t) { const int k = cx.lane + 32 * t; if (k < len && uc[t] != 0.0) rb[r * stride + k] = OGS_FMA(sm[r], uc[t], rb[r * stride + k]); }
+                if (cx.lane == 0) rb[r * stride + p] = rp[r] + sm[r] * up;
+            }
+        }
+        cx.wsync();
+    }
 }
 
 // ---------------------------------------------------------------- NNLS (Lawson & Hanson, chapter 23)
@@ -480,6 +539,7 @@ OGS_FN int ogs_lsei(Cx& cx, OgsQp& Q) {
         ogs_reflect_matrix(cx, Q.C + (size_t)(i + 1) * ld, ld, mc - i - 1, row, i, nq, Q.ups[i], Q.binv[i]);
         cx.sync();
     }
+    if (cx.tid == 0) Q.clk[17] += (double)(cx.clock() - t0c);        // (phase 1 alone)
     //      Phase 2: the rows of E and G are independent of each other: a warp keeps `wrows` of them in shared
     //      memory and takes them through H_0 .. H_{mc-1} without a block barrier or a global round trip per step.
     {
@@ -494,7 +554,8 @@ OGS_FN int ogs_lsei(Cx& cx, OgsQp& Q) {
                 for (int k = cx.lane; k < nq; k += cx.wsize) rb[r * stride + k] = (r < cnt) ? src[k] : 0.0;
             }
             cx.wsync();
-            if (R == 4) ogs_reflect_buffer<4>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
+            if (Cx::kLanes32 && (cx.flags & 1) && R == 4 && nq <= 256) ogs_reflect_buffer_reg<4, 8>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
+            else if (R == 4) ogs_reflect_buffer<4>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
             else if (R == 2) ogs_reflect_buffer<2>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
             else ogs_reflect_buffer<1>(cx, rb, stride, Q.C, ld, Q.ups, Q.binv, 0, mc, nq);
             for (int r = 0; r < cnt; ++r) {

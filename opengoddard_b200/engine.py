@@ -570,7 +570,7 @@ def lgl_device(N, device="cuda:0"):
 
 
 SQP_SCALARS = ("f", "f0", "gs", "h1", "h2", "h3", "h4", "t", "t0", "alpha", "mode", "iter", "reset", "line",
-               "inconsistent", "nfev", "njev", "_17", "clk_build", "clk_lsei", "clk_lsi", "clk_nnls", "clk_finish", "clk_bfgs")
+               "inconsistent", "nfev", "njev", "clk_lsei_phase1", "clk_build", "clk_lsei", "clk_lsi", "clk_nnls", "clk_finish", "clk_bfgs")
 
 
 class SqpKernel:

@@ -27,6 +27,8 @@ with eng.device_sqp(S, 1e-6, maxiter) as dq:
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     clk = dq.k.scalars(S)
+    print("LSEI phase 1 (triangularise C) share of LSEI: %.2f" % (float(clk["clk_lsei_phase1"].sum()) / float(clk["clk_lsei"].sum())))
+    clk = {k: v for k, v in clk.items() if k != "clk_lsei_phase1"}
     tot = sum(float(clk[k].sum()) for k in clk if k.startswith("clk_"))
     print("SM cycles per phase (share):", {k[4:]: "%.1f%%" % (100 * float(clk[k].sum()) / tot) for k in clk if k.startswith("clk_")},
           " mean cycles per instance-iteration: %.0f" % (tot / max(1, int(res["nit"].sum()))))
