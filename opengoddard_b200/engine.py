@@ -651,6 +651,10 @@ class DeviceSqp:
     def __init__(self, eng, max_batch, ftol=1e-6, maxiter=25):
         self.eng, self.torch = eng, eng.torch
         M, n = eng.nrows, eng.nvars
+        if n > 512:
+            warnings.warn("OpenGoddard-B200: the device SLSQP keeps one instance's QP matrices per thread block in L2; at "
+                          "%d variables a QP streams them from HBM and is no faster than the host SLSQP pool "
+                          "(solve_batch's default)" % n, RuntimeWarning, stacklevel=3)
         lin = eng.jac_pattern().astype(np.int64)
         colptr = np.searchsorted(lin, np.arange(n + 1, dtype=np.int64) * M)
         self.k = SqpKernel(eng.b, eng.torch, eng.device, n, M - 1, eng.meq, colptr, lin % M, eng.lb.cpu().numpy(),

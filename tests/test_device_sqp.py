@@ -197,6 +197,13 @@ def test_device_sqp_matches_the_restatement(name):
     assert np.abs(out["x"] - ref["x"]).max() <= 1e-8 * max(1.0, np.abs(ref["x"]).max())
 
 
+def test_solve_batch_rejects_an_unknown_qp_before_touching_the_gpu(api):
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    with pytest.raises(ValueError):
+        wl.prob.solve_batch(np.asarray(wl.prob.p)[None], wl.obj, qp="cvx")
+
+
 # ---------------------------------------------------------------- the CUDA kernel (thread block per instance)
 def _kernel(n, m, meq, colptr, prow, lb, ub, ftol, maxiter, B):
     import torch
