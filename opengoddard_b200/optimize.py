@@ -467,7 +467,10 @@ class Problem:
         if qp not in ("scipy", "device"):
             raise ValueError("qp must be 'scipy' or 'device'")
         if qp == "device" and self.cost_derivative is not None:
-            raise NotImplementedError("qp='device' differentiates the cost on the device; cost_derivative is not used")
+            import warnings
+            warnings.warn("OpenGoddard-B200: solve_batch(qp='device') takes the cost gradient from the device Jacobian "
+                          "(finite differences, or exact with jacobian='exact'); the Python cost_derivative is not called",
+                          RuntimeWarning, stacklevel=2)
         eng = self._engine_for(obj)
         P0 = np.array(np.atleast_2d(P0), dtype=np.float64)
         return batch.run_sharded(
