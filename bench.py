@@ -340,12 +340,12 @@ def tensor_check(eng, wl, P, torch):
         pipe = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k1_tensor_pipe_pct")
     except (OSError, ValueError):
         pass
-    return {"kernel": "ogb_dx_gemm_kernel (K1, mma.sync m8n8k4 f64 = DMMA; tcgen05 has no f64 kind)",
+    return {"kernel": "ogb_dx_gemm2_kernel (K1, mma.sync m8n8k4 f64 = DMMA; tcgen05 has no f64 kind)",
             "flop_per_launch": flop, "k1_ms_alone": k1, "k1_tflops": flop / (k1 * 1e-3) / 1e12,
             "dgemm_peak_tflops": peak, "dgemm_peak_how": "torch.matmul float64 4096^3 (cuBLAS), best of 5, CUDA events",
             "frac": flop / (k1 * 1e-3) / 1e12 / peak, "pipe_pct_from_ncu": pipe,
-            "note": "K1 is 2 N^2 nstates FLOP per instance (15 kFLOP at Goddard-50): memory / latency bound by "
-                    "construction, ~5 % of a step"}
+            "note": "K1 is 2 N^2 nstates FLOP per instance (15 kFLOP at Goddard-50): one wave of warps, latency bound "
+                    "by construction, ~3 % of a step"}
 
 
 def extras(eng, wl, cfg, workloads, P, P_host, torch, args, api):

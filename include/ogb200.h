@@ -190,8 +190,10 @@ enum ogb_option {
                                     zeros of the CTA's next work item while the other warps compute (measured slower);
                                     16 = with an odd number of rows a warp takes two adjacent columns and zeroes them
                                     as one 16-byte-aligned span (no 8-byte stores at the column ends)                 */
-    OGB_OPT_GEMM_UNIT = 13,      /* K1 work unit: 0 / 8 (default) = an 8-row tile computes whole rows of D.X; 2 = (8-row tile,
-                                    16 output nodes) units (experiment: more warps in flight, measured slower)       */
+    OGB_OPT_GEMM_UNIT = 13,      /* K1 form: 0 (default) = the latency-organised kernel (compile-time strides, cp.async
+                                    staging, hoisted unit division; phases of <= 128 nodes); 8 = the round-1 kernel, an
+                                    8-row tile computes whole rows of D.X; 2 = its (8-row tile, 16 output nodes) units
+                                    (experiment, measured slower).  All three give the same bits                     */
     OGB_OPT_FUSED_DX = 4         /* 0: K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two launches); 1: the sweep
                                     kernel computes D.X itself with in-kernel DMMAs (one launch; bit-identical);
                                     -1 (default): automatic -- one launch for batches of at most half a wave of CTAs

@@ -87,6 +87,31 @@ def test_dx_gemm_tensor_core(torch_cuda, api, name):
     assert np.abs(DX - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("name", ["cfg2_goddard50", "cfg3_goddard_knot30x2", "cfg4_polar3x40", "cfg5_lowthrust128",
+                                  "edge_stress_mixed", "edge_stress_small"])
+def test_dx_gemm_forms_bit_identical(torch_cuda, api, name):
+    """The latency-organised K1 (default: compile-time strides, cp.async staging, the u-only part of the IEEE
+    division `(x * u) / u` hoisted per row) against the round-1 kernel (OGB_OPT_GEMM_UNIT = 8, plain `/`): same
+    DMMAs in the same order, so the same bits -- also where the hoisted division has to fall back to the built-in
+    one (zeros, denormals, huge values, infinities) and with / without the clip."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build(name, api)
+    eng = wl.prob.compile(wl.obj)
+    P = workloads.make_batch(wl, 203)
+    rng = np.random.default_rng(5)
+    odd = np.array([0.0, -0.0, 5e-324, -3e-310, 1e-300, -1e-290, 1e-250, 1e250, -1e290, 1e300, 1.7e308, np.inf,
+                    1.0, -1.0, 2.0 ** -1000, 2.0 ** 1000, 3.0])
+    mask = rng.random(P.shape) < 0.2
+    P[mask] = rng.choice(odd, size=int(mask.sum()))
+    Pd = torch_cuda.from_numpy(P).cuda()
+    for clip in (False, True):
+        eng.set_option(13, 8)
+        old = eng.dx_gemm(Pd, clip=clip).clone()
+        eng.set_option(13, 0)
+        new = eng.dx_gemm(Pd, clip=clip)
+        assert torch_cuda.equal(old.view(torch_cuda.int64), new.view(torch_cuda.int64))
+
+
 @pytest.mark.parametrize("name,B", [("cfg2_goddard50", 64), ("cfg3_goddard_knot30x2", 33),
                                     ("cfg5_lowthrust128", 9), ("cfg4_polar3x40", 7),
                                     ("edge_two_stage_no_inequality", 5), ("edge_stress_mixed", 3),

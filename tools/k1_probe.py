@@ -1,5 +1,6 @@
-"""Round-2 probe: K1 (D.X batched FP64 DMMA GEMM) with whole-row work units (OGB_OPT_GEMM_UNIT = 8) against
-(8-row tile, 16 output nodes) units (= 2): more, shorter units for this latency-bound kernel.  Bit-identical.
+"""Round-2 probe: K1 (D.X batched FP64 DMMA GEMM): the round-1 kernel with whole-row work units (OGB_OPT_GEMM_UNIT = 8;
+= 2 selects its 16-node units, measured slower earlier) against the latency-organised form (0, default: p loads first,
+cp.async staging of D and the bounds, software-pipelined chunks).  Bit-identical.
     python tools/k1_probe.py"""
 import os
 import sys
@@ -17,7 +18,7 @@ for name, B in (("cfg2_goddard50", 4096), ("cfg2_goddard50", 1024), ("cfg3_godda
     eng = wl.prob.compile(wl.obj)
     P = torch.from_numpy(workloads.make_batch(wl, B)).cuda()
     ref = None
-    for unit in (8, 2, 0):
+    for unit in (8, 0):
         eng.set_option(13, unit)
         DX = eng.dx_gemm(P, clip=True)
         best = 1e9
