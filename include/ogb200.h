@@ -194,6 +194,8 @@ enum ogb_option {
                                     staging, hoisted unit division; phases of <= 128 nodes); 8 = the round-1 kernel, an
                                     8-row tile computes whole rows of D.X; 2 = its (8-row tile, 16 output nodes) units
                                     (experiment, measured slower).  All three give the same bits                     */
+    OGB_OPT_PDL = 14,            /* 1 (default): the sweep kernel is launched behind K1 with programmatic stream
+                                    serialization (its launch and per-CTA prologue overlap K1; results unchanged)  */
     OGB_OPT_FUSED_DX = 4         /* 0: K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two launches); 1: the sweep
                                     kernel computes D.X itself with in-kernel DMMAs (one launch; bit-identical);
                                     -1 (default): automatic -- one launch for batches of at most half a wave of CTAs

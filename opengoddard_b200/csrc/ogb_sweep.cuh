@@ -153,6 +153,11 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
         }
     }
     __syncthreads();
+    // Programmatic dependent launch (ogb_eval_fd launches this kernel with programmatic stream serialization right
+    // after K1, which signals at its start): everything above -- the problem's own read-only tables -- may run
+    // while K1 is still computing D.X; p, D.X, c and J are touched only after K1 has completed and flushed.
+    // Without such a launch this is a no-op.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int n = P.n, M = P.M, ndx = P.ndx;
     // Writer warps (OGB_OPT_ZERO_MODE bits 2-3; dense FD output only): the last one or two warps of the CTA do
