@@ -112,6 +112,36 @@ def test_dx_gemm_forms_bit_identical(torch_cuda, api, name):
         assert torch_cuda.equal(old.view(torch_cuda.int64), new.view(torch_cuda.int64))
 
 
+@pytest.mark.parametrize("nodes", [(5, 12), (17, 24), (30, 31), (40, 33), (41, 48), (50, 56), (64, 57), (65, 90),
+                                   (96, 20), (97, 128), (128, 3), (129, 16)])
+def test_dx_gemm_every_instantiation(torch_cuda, api, nodes):
+    """Every instantiation of the latency-organised K1 (NT = 2 ... 8 tiles with the 68-double stride, 12 / 16 with the
+    132-double stride; 129 nodes fall back to the round-1 kernel) on a two-phase problem with a non-unit state unit:
+    against a plain fp64 matmul, and bit for bit against the round-1 kernel; odd batch sizes leave partial tiles."""
+    from opengoddard_b200 import workloads
+    wl = workloads.goddard_knot(api, nodes=nodes)
+    prob = wl.prob
+    eng = prob.compile(wl.obj, jit=False)
+    for B in (1, 37):
+        P = workloads.make_batch(wl, B)
+        Pd = torch_cuda.from_numpy(P).cuda()
+        eng.set_option(13, 8)
+        old = eng.dx_gemm(Pd, clip=True).clone()
+        eng.set_option(13, 0)
+        new = eng.dx_gemm(Pd, clip=True)
+        assert torch_cuda.equal(old, new)
+        lb, ub = workloads.bounds_arrays(prob)
+        Pc = np.clip(P, lb, ub)
+        ref = []
+        for s in range(prob.number_of_section):
+            for a in range(prob.number_of_states[s]):
+                lo = prob.index_states(a, s)
+                u = prob.unit_states[s][a]
+                ref.append(((Pc[:, lo:lo + prob.nodes[s]] * u) / u) @ prob.D[s].T)
+        ref = np.concatenate(ref, axis=1)
+        assert np.abs(new.cpu().numpy() - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("name,B", [("cfg2_goddard50", 64), ("cfg3_goddard_knot30x2", 33),
                                     ("cfg5_lowthrust128", 9), ("cfg4_polar3x40", 7),
                                     ("edge_two_stage_no_inequality", 5), ("edge_stress_mixed", 3),
