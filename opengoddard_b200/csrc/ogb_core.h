@@ -133,6 +133,10 @@ struct OgbPlan {
     int nbuf;           // dense column buffers per warp
     unsigned long long smem_bytes;  // dynamic shared memory
     int ctas_per_sm;
+    // Tail refinement (chosen per launch): instances [0, head) are cut into `split` work items of `group` columns,
+    // instances [head, B) -- claimed last -- into `tsplit` items of `tgroup` columns, so the persistent CTAs finish
+    // within one SMALL item of each other.  head >= B: no refinement.
+    int head, tsplit, tgroup;
     // offsets (in doubles) into the dynamic shared memory block
     unsigned long long o_cache, o_sp, o_sdx, o_sbase, o_sc, o_scbase, o_coef, o_prefix, o_pert, o_pdx, o_px1,
         o_pdlt, o_pcol, o_scpert, o_cf, o_rterm, o_costp, o_prdx, o_slot, o_gpert, o_tiles, tile_stride, o_tail,

@@ -112,6 +112,7 @@ static inline bool ogb_make_plan(const OgbProb& P, size_t ncode, size_t nconsts,
     const int GMAX = gmax > 0 ? gmax : 256;          // Jacobian columns staged per work item (measured: tools/sweep_group.py)
     pl->split = (P.n + GMAX - 1) / GMAX;
     pl->G = (P.n + pl->split - 1) / pl->split;
+    pl->head = 0x7fffffff; pl->tsplit = pl->split; pl->tgroup = pl->G;
     pl->group = pl->G;
     // pick the CTA size (2..8 warps) that keeps the most warps resident per SM; registers
     // allow 768 threads per SM (<= 85 registers per thread)

@@ -168,15 +168,33 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     // barrier of the item loop involves the compute warps only.
     const int nwr = (PACKED_OUT == 0 && with_fd == 1 && (zero_mode & 12) && (nthr >> 5) >= 4) ? ((zero_mode & 8) ? 2 : 1) : 0;
     const int cwarps = (nthr >> 5) - nwr, cnthr = cwarps * 32;        // compute warps / threads
-    const int nchunk = with_fd ? pl.split : 1;
-    const long nitems = (long)B * nchunk;
+    // work item -> (instance, first column, columns): the instances below `head` in `nchunk` items of pl.group
+    // columns, the trailing ones (claimed last) in `tchunk` finer items of pl.tgroup columns (tail refinement)
+    const int nchunk = with_fd ? pl.split : 1, tchunk = with_fd ? pl.tsplit : 1;
+    const long nheadb = pl.head < B ? pl.head : B;
+    const long nhead_items = nheadb * nchunk;
+    const long nitems = nhead_items + ((long)B - nheadb) * tchunk;
+    auto item_instance = [&](long item) -> long {
+        return item < nhead_items ? item / nchunk : nheadb + (item - nhead_items) / tchunk;
+    };
+    auto item_columns = [&](long item, long b, int& jlo, int& ncols) -> int {     // returns the chunk index
+        if (!with_fd) { jlo = 0; ncols = 0; return 0; }
+        if (item < nhead_items) {
+            const int ch = (int)(item - b * nchunk);
+            jlo = ch * pl.group; ncols = min(pl.group, P.n - jlo);
+            return ch;
+        }
+        const int ch = (int)((item - nhead_items) - (b - nheadb) * tchunk);
+        jlo = ch * pl.tgroup; ncols = min(pl.tgroup, P.n - jlo);
+        return ch;
+    };
     const bool fused_dx = DX == nullptr;            // D.X by in-kernel DMMA instead of K1's scratch
     const size_t in_stride = pl.o_sdx - pl.o_sp + ((size_t)(ndx + 2 + 1) & ~(size_t)1);   // doubles per input stage
 
     // TMA bulk loads of p[b] and D.X[b] into input stage `st` (16-byte aligned body; an odd
     // leading / trailing double is fetched with a plain load by another warp)
     auto stage_inputs = [&](long item, int st) {
-        const long b = item / nchunk;
+        const long b = item_instance(item);
         const double* gp = p + b * n;
         const double* gdx = fused_dx ? nullptr : DX + b * ndx;
         const int hp = (int)((reinterpret_cast<uintptr_t>(gp) >> 3) & 1);
@@ -211,9 +229,9 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     };
     // zeros of one work item's region J[b, jlo .. jlo + ncols, :] by `nw` warps (this thread: lane of warp `w`)
     auto zero_item = [&](long item, int w, int nw) {
-        const long zb = item / nchunk;
-        const int zch = (int)(item - zb * nchunk);
-        const int zlo = zch * pl.group, zn = min(pl.group, n - zlo);
+        const long zb = item_instance(item);
+        int zlo, zn;
+        item_columns(item, zb, zlo, zn);
         double* reg = J + (size_t)zb * n * (size_t)M + (size_t)zlo * (size_t)M;
         const size_t len = (size_t)zn * (size_t)M;
         const size_t hj = (reinterpret_cast<uintptr_t>(reg) >> 3) & 1;
@@ -243,10 +261,9 @@ ogb_sweep_kernel(OgbProb P, OgbPlan pl, const double* __restrict__ p, const doub
     csync();                 // the odd head / tail doubles of the first item are in place
     unsigned it = 0;
     for (long item = blockIdx.x; item < nitems; ++it) {
-        const long b = item / nchunk;
-        const int ch = (int)(item - b * nchunk);
-        const int jlo = with_fd ? ch * pl.group : 0;
-        const int ncols = with_fd ? min(pl.group, n - jlo) : 0;
+        const long b = item_instance(item);
+        int jlo, ncols;
+        const int ch = item_columns(item, b, jlo, ncols);
         const int st = (int)(it & 1u);
         long claimed = 0;
         if (tid == 0)

@@ -142,6 +142,27 @@ def test_dx_gemm_every_instantiation(torch_cuda, api, nodes):
         assert np.abs(new.cpu().numpy() - ref).max() <= 1e-11 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("name", ["cfg2_goddard50", "cfg5_lowthrust128", "edge_stress_mixed"])
+def test_tail_refinement_bit_identical(torch_cuda, api, name):
+    """OGB_OPT_TAIL_REFINE: the last instances of a large batch are cut into finer work items (claimed last, so the
+    persistent CTAs finish together).  Forced here on a small batch by capping the persistent grid at 8 CTAs; the
+    Jacobians must not change by a bit, whatever share of the batch is refined."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build(name, api)
+    eng = wl.prob.compile(wl.obj)
+    P = workloads.make_batch(wl, 67)
+    eng.set_option(15, 0)
+    c0, J0 = eng.eval_fd(P)
+    eng.set_option(3, 8)
+    for pct in (0, 40, 100, 250, 400):
+        eng.set_option(15, pct)
+        c1, J1 = eng.eval_fd(P)
+        assert torch_cuda.equal(c0, c1) and torch_cuda.equal(J0, J1), pct
+    eng.set_option(2, 0)                        # the interpreter kernel
+    c2, J2 = eng.eval_fd(P)
+    assert torch_cuda.equal(c0, c2) and torch_cuda.equal(J0, J2)
+
+
 @pytest.mark.parametrize("name,B", [("cfg2_goddard50", 64), ("cfg3_goddard_knot30x2", 33),
                                     ("cfg5_lowthrust128", 9), ("cfg4_polar3x40", 7),
                                     ("edge_two_stage_no_inequality", 5), ("edge_stress_mixed", 3),
