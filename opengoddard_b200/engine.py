@@ -82,7 +82,8 @@ class DeviceProblem:
     def set_option(self, key, value):
         """ogb_problem_set_option (include/ogb200.h): 0 generic columns, 1 threads, 2 jit,
         3 grid cap, 4 fused D.X, 9 split pipeline (-1 auto / 0 fused / 1 split), 10 split chunk,
-        11 streaming zero stores in K2b."""
+        11 streaming zero stores in K2b, 12 zero mode, 13 K1 form (0 latency-organised / 8 round-1 kernel),
+        14 programmatic dependent launch of the sweep behind K1, 15 tail refinement (per cent of a wave)."""
         self._rc(self.b.lib.ogb_problem_set_option(self.h, int(key), int(value)), "ogb_problem_set_option")
         if int(key) == 4:
             self.fused_dx = int(value)
