@@ -1,5 +1,6 @@
 """Small run for compute-sanitizer: every device path of rounds 1 and 2 on a few problems -- the fused sweep kernel
-(JIT, interpreter, generic columns, D.X fused and not, writer-warp mode), the packed sweep (K2a), the exact mode,
+(JIT, interpreter, generic columns, D.X fused and not, writer-warp mode, tail refinement, with and without
+programmatic dependent launch), both forms of K1, the packed sweep (K2a), the exact mode,
 densify (K2b), the split pipeline, K3, the host session (dense / packed / scatter), guess / jitter / trajectories.
     compute-sanitizer --tool memcheck python tools/sanitize_check.py"""
 import sys
@@ -30,6 +31,16 @@ for name in ("cfg2_goddard50", "cfg3_goddard_knot30x2", "edge_stress_small", "ed
     eng.set_option(12, 4)
     cw, Jw = eng.eval_fd(P)                       # writer warps
     eng.set_option(12, 0)
+    eng.set_option(3, 1); eng.set_option(15, 200)
+    ct, Jt = eng.eval_fd(P)                       # tail refinement (one persistent CTA: the last two instances refined)
+    eng.set_option(3, 0); eng.set_option(15, 100)
+    eng.set_option(13, 8)
+    DXo = eng.dx_gemm(P, clip=True).clone()       # the round-1 K1
+    eng.set_option(13, 0)
+    DXn = eng.dx_gemm(P, clip=True)               # the latency-organised K1
+    eng.set_option(14, 0)
+    cq, Jq = eng.eval_fd(P)                       # plain launch of the sweep behind K1 (no PDL)
+    eng.set_option(14, 1)
     _, v1 = eng.eval_sparse(P)                    # K2a (JIT)
     _, e1 = eng.eval_exact(P)                     # exact (JIT)
     Jd = eng.densify(v1)                          # K2b
@@ -50,7 +61,7 @@ for name in ("cfg2_goddard50", "cfg3_goddard_knot30x2", "edge_stress_small", "ed
     G = eng.guess_batch([("linear", 0, None), ("cubic", 1, 0)], np.ones((3, 2, 4)), wl.prob.time_all_section)
     torch.cuda.synchronize()
     Jn = J1.cpu().numpy()
-    ok = [torch.equal(J0, J1), torch.equal(Jf, J1), torch.equal(Jg, J1), torch.equal(Jw, J1), torch.equal(Jd, J1),
+    ok = [torch.equal(Jt, J1), torch.equal(DXo, DXn), torch.equal(Jq, J1), torch.equal(J0, J1), torch.equal(Jf, J1), torch.equal(Jg, J1), torch.equal(Jw, J1), torch.equal(Jd, J1),
           torch.equal(Js, J1), torch.equal(v0, v1), torch.equal(v1, J1.reshape(B, -1)[:, lin]), torch.equal(vk, v1),
           bool((Jh == Jn).all()), bool((V == v1.cpu().numpy()).all()),
           all((Cs[b] == Jn[b, :, :m].T).all() and (gs[b] == Jn[b, :, m]).all() for b in range(B)),
