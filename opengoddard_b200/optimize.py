@@ -395,15 +395,20 @@ class Problem:
             raise ValueError("no compiled engine yet: pass `obj`")
         return self.compile(obj, device=device, jit=jit)
 
-    def evaluate_batch(self, P, obj=None, jacobian=True, host=False):
+    def evaluate_batch(self, P, obj=None, jacobian=True, host=False, autotune=False):
         """Batched hot path: P (B, nvars) -> c (B, m+1) [, J (B, nvars, m+1)] as torch CUDA
         tensors; row m carries cost / grad cost.  J[b, j, :] is column j.  host=True: P is a host
         array and the results come back as numpy arrays in host memory through the host-buffer
         session (ogb_host_eval_fd: packed device->host transport, dense J rebuilt by host threads).
         jacobian: True = SciPy's forward differences (the reference's Jacobian), "sparse" = the same as
         packed values (B, nnz) in the engine's jac_pattern() layout, "exact" = the exact Jacobian (analytic
-        collocation block + forward-mode tangents of the callbacks; opt-in, packed), False = c only."""
+        collocation block + forward-mode tangents of the callbacks; opt-in, packed), False = c only.
+        autotune=True (dense FD Jacobian on the device only): the first call on a compiled problem times the sweep
+        kernel's CTA widths on P (DeviceProblem.autotune: the best width is problem-dependent, up to 18 % on the
+        BASELINE problems) and keeps the choice for later calls; results do not depend on it."""
         eng = self._engine_for(obj)
+        if autotune and jacobian is True and not host and getattr(eng, "tuned_threads", None) is None and len(P) > 0:
+            eng.autotune(P)
         if jacobian in ("exact", "sparse"):
             if host:
                 ev = eng.host_evaluator(exact=jacobian == "exact")

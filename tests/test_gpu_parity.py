@@ -360,6 +360,23 @@ def test_solve_batch_with_worker_processes(torch_cuda, api, capsys):
     assert (two["nit"] > 0).all()
 
 
+def test_evaluate_batch_autotune_keyword(torch_cuda, api):
+    """Problem.evaluate_batch(..., autotune=True): the first dense-FD call tunes the sweep kernel's CTA width on
+    the batch, later calls keep it; c and J are those of the untuned engine."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    P = workloads.make_batch(wl, 64)
+    c0, J0 = wl.prob.evaluate_batch(P, wl.obj)
+    eng = wl.prob._engine
+    assert getattr(eng, "tuned_threads", None) is None
+    c1, J1 = wl.prob.evaluate_batch(P, wl.obj, autotune=True)
+    assert wl.prob._engine is eng and eng.tuned_threads in (128, 256, 384)
+    launches = eng.launches
+    c2, J2 = wl.prob.evaluate_batch(P, wl.obj, autotune=True)          # already tuned: one evaluation, no timing runs
+    assert eng.launches - launches <= 2
+    assert torch_cuda.equal(c0, c1) and torch_cuda.equal(J0, J1) and torch_cuda.equal(c0, c2) and torch_cuda.equal(J0, J2)
+
+
 def test_autotune_keeps_results_bit_identical(torch_cuda, api):
     """DeviceProblem.autotune times the 256- and 384-thread builds of the sweep kernel and keeps one;
     c and J do not depend on the choice."""
