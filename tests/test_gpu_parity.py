@@ -112,6 +112,32 @@ def test_dx_gemm_forms_bit_identical(torch_cuda, api, name):
         assert torch_cuda.equal(old.view(torch_cuda.int64), new.view(torch_cuda.int64))
 
 
+def test_dx_gemm_persistent_loop(torch_cuda, api):
+    """More 8-row tiles than resident warps (brachistochrone-20 x 20 000: 7 500 tiles on at most 2 368 warps): every
+    warp of K1 walks several tiles, requesting the next tile's rows before the DMMAs of the current one.  Against the
+    round-1 kernel, bit for bit, and a few rows against numpy."""
+    from opengoddard_b200 import workloads
+    wl = workloads.build("cfg1_brachistochrone20", api)
+    prob = wl.prob
+    eng = prob.compile(wl.obj, jit=False)
+    B = 20000
+    P = np.tile(workloads.make_batch(wl, 500), (B // 500, 1))
+    P *= (1.0 + 1e-3 * np.arange(B)[:, None] / B)
+    Pd = torch_cuda.from_numpy(P).cuda()
+    eng.set_option(13, 8)
+    old = eng.dx_gemm(Pd, clip=True).clone()
+    eng.set_option(13, 0)
+    new = eng.dx_gemm(Pd, clip=True)
+    assert torch_cuda.equal(old, new)
+    lb, ub = workloads.bounds_arrays(prob)
+    rows = [0, 1, 7, 8, 2367, 2368, 9999, B - 1]
+    Pc = np.clip(P[rows], lb, ub)
+    ref = np.concatenate([((Pc[:, prob.index_states(a, 0):prob.index_states(a, 0) + prob.nodes[0]]
+                            * prob.unit_states[0][a]) / prob.unit_states[0][a]) @ prob.D[0].T
+                          for a in range(prob.number_of_states[0])], axis=1)
+    assert np.abs(new[rows].cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("nodes", [(5, 12), (17, 24), (30, 31), (40, 33), (41, 48), (50, 56), (64, 57), (65, 90),
                                    (96, 20), (97, 128), (128, 3), (129, 16)])
 def test_dx_gemm_every_instantiation(torch_cuda, api, nodes):
