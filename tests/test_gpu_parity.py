@@ -169,7 +169,7 @@ def test_dx_gemm_every_instantiation(torch_cuda, api, nodes):
 
 
 @pytest.mark.parametrize("name", ["cfg2_goddard50", "cfg5_lowthrust128", "edge_stress_mixed"])
-def test_tail_refinement_bit_identical(torch_cuda, api, name):
+def test_tail_refinement_and_pdl_bit_identical(torch_cuda, api, name):
     """OGB_OPT_TAIL_REFINE: the last instances of a large batch are cut into finer work items (claimed last, so the
     persistent CTAs finish together).  Forced here on a small batch by capping the persistent grid at 8 CTAs; the
     Jacobians must not change by a bit, whatever share of the batch is refined."""
@@ -187,6 +187,15 @@ def test_tail_refinement_bit_identical(torch_cuda, api, name):
     eng.set_option(2, 0)                        # the interpreter kernel
     c2, J2 = eng.eval_fd(P)
     assert torch_cuda.equal(c0, c2) and torch_cuda.equal(J0, J2)
+    # OGB_OPT_PDL: the sweep kernel launched behind K1 programmatically (default) or plainly -- same results
+    eng.set_option(3, 0)
+    eng.set_option(4, 0)                        # (K1 + K2 also for this small batch)
+    for jit in (1, 0):
+        eng.set_option(2, jit)
+        for pdl in (0, 1):
+            eng.set_option(14, pdl)
+            c3, J3 = eng.eval_fd(P)
+            assert torch_cuda.equal(c0, c3) and torch_cuda.equal(J0, J3), (jit, pdl)
 
 
 @pytest.mark.parametrize("name,B", [("cfg2_goddard50", 64), ("cfg3_goddard_knot30x2", 33),
