@@ -198,7 +198,8 @@ enum ogb_option {
                                     serialization (its launch and per-CTA prologue overlap K1; results unchanged)  */
     OGB_OPT_TAIL_REFINE = 15,    /* tail refinement of the dense FD sweep: the last instances of a large batch (this
                                     many per cent of one wave of work items) are cut into items of >= 64 columns so
-                                    the persistent CTAs finish together; default 100, 0 = off.  Results unchanged   */
+                                    the persistent CTAs finish together; 0 = off; -1 (default) = 100 for problems with
+                                    light node programs (<= 64 tape operations), off for heavy ones.  Results unchanged */
     OGB_OPT_FUSED_DX = 4         /* 0: K1 ogb_dx_gemm writes the D.X scratch, then the sweep (two launches); 1: the sweep
                                     kernel computes D.X itself with in-kernel DMMAs (one launch; bit-identical);
                                     -1 (default): automatic -- one launch for batches of at most half a wave of CTAs
