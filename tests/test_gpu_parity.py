@@ -112,6 +112,30 @@ def test_dx_gemm_forms_bit_identical(torch_cuda, api, name):
         assert torch_cuda.equal(old.view(torch_cuda.int64), new.view(torch_cuda.int64))
 
 
+@pytest.mark.parametrize("units", [(1e-200, 3.0, 1.0), (2.0 ** -1000, 2.0 ** 1000, 0.1), (-3.0, 1e300, 7e-310),
+                                   (1.0 - 2.0 ** -53, 1.0 + 2.0 ** -52, 2.0 - 2.0 ** -52), (1e17, 3e-17, 123456.789)])
+def test_dx_gemm_odd_units(torch_cuda, api, units):
+    """The hoisted unit division of K1 with units far from anything a user would set (tiny, huge, negative,
+    denormal, significands of all ones): wherever its exponent tests do not guarantee the compiler's fast path
+    it must hand over to the built-in division -- the result is the round-1 kernel's, bit for bit (NaN / Inf
+    patterns included)."""
+    from opengoddard_b200 import workloads
+    wl = workloads.goddard_knot(api, nodes=(21, 50))
+    for k, u in enumerate(units):
+        wl.prob.set_unit_states_all_section(k, u)
+    eng = wl.prob.compile(wl.obj, jit=False)
+    P = workloads.make_batch(wl, 41)
+    rng = np.random.default_rng(11)
+    mask = rng.random(P.shape) < 0.15
+    P[mask] = rng.choice(np.array([0.0, -0.0, 5e-324, 1e-300, -1e-250, 1e250, -1e300, 1.0, 3.0]), size=int(mask.sum()))
+    Pd = torch_cuda.from_numpy(P).cuda()
+    eng.set_option(13, 8)
+    old = eng.dx_gemm(Pd).clone()
+    eng.set_option(13, 0)
+    new = eng.dx_gemm(Pd)
+    assert torch_cuda.equal(old.view(torch_cuda.int64), new.view(torch_cuda.int64))
+
+
 def test_dx_gemm_persistent_loop(torch_cuda, api):
     """More 8-row tiles than resident warps (brachistochrone-20 x 20 000: 7 500 tiles on at most 2 368 warps): every
     warp of K1 walks several tiles, requesting the next tile's rows before the DMMAs of the current one.  Against the
