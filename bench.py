@@ -342,6 +342,8 @@ def tensor_check(eng, wl, P, torch):
         pass
     return {"kernel": "ogb_dx_gemm2_kernel (K1, mma.sync m8n8k4 f64 = DMMA; tcgen05 has no f64 kind)",
             "flop_per_launch": flop, "k1_ms_alone": k1, "k1_tflops": flop / (k1 * 1e-3) / 1e12,
+            "k1_ms_alone_how": "one launch between two CUDA events on an idle stream, best of 10: includes the launch "
+                               "latency of an idle GPU; k1_ms_in_step (ms_per_step - K2 alone, cold L2) is what a step pays",
             "dgemm_peak_tflops": peak, "dgemm_peak_how": "torch.matmul float64 4096^3 (cuBLAS), best of 5, CUDA events",
             "frac": flop / (k1 * 1e-3) / 1e12 / peak, "pipe_pct_from_ncu": pipe,
             "note": "K1 is 2 N^2 nstates FLOP per instance (15 kFLOP at Goddard-50): one wave of warps, latency bound "
