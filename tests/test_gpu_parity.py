@@ -211,6 +211,10 @@ def test_tail_refinement_and_pdl_bit_identical(torch_cuda, api, name):
     eng.set_option(2, 0)                        # the interpreter kernel
     c2, J2 = eng.eval_fd(P)
     assert torch_cuda.equal(c0, c2) and torch_cuda.equal(J0, J2)
+    eng.set_option(5, 0)                        # static item assignment instead of the atomic ticket
+    c2, J2 = eng.eval_fd(P)
+    eng.set_option(5, 1)
+    assert torch_cuda.equal(c0, c2) and torch_cuda.equal(J0, J2)
     # OGB_OPT_PDL: the sweep kernel launched behind K1 programmatically (default) or plainly -- same results
     eng.set_option(3, 0)
     eng.set_option(4, 0)                        # (K1 + K2 also for this small batch)
